@@ -1,0 +1,82 @@
+"""ctypes binding of lib3dvlp_b200.so (C ABI: include/pointnet2_b200.h).
+
+There is deliberately NO fallback: if the CUDA library has not been built, or a tensor lives on the
+CPU, the call fails loudly.  (The reference has no CPU path either:
+lib/pointnet2/_ext_src/src/sampling.cpp:38-40 ``TORCH_CHECK(false, "CPU not supported")``.)
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib3dvlp_b200.so")
+
+_lib = None
+
+
+class Pn2Error(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "3dvlp_b200: CUDA library %s is missing -- build it with `python 3dvlp_b200/build.py` "
+                "(or __graft_entry__.build()).  There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.pn2_last_error.restype = ctypes.c_char_p
+        L.pn2_abi_version.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def stream_of(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def call(name, *args, device=None):
+    """Invoke one C-ABI entry point on `device` (made current for the call) and raise on failure."""
+    L = lib()
+    fn = getattr(L, name)
+    if device is not None and device.index is not None and device.index != torch.cuda.current_device():
+        with torch.cuda.device(device):
+            rc = fn(*args)
+    else:
+        rc = fn(*args)
+    if rc != 0:
+        raise Pn2Error("%s failed (status %d): %s" % (name, rc, L.pn2_last_error().decode()))
+
+
+# ---- argument checks with the reference's messages (include/utils.h:10-30) -----------------------
+
+def check_contiguous(t, name):
+    if not t.is_contiguous():
+        raise RuntimeError(name + " must be a contiguous tensor")
+
+
+def check_float(t, name):
+    if t.dtype != torch.float32:
+        raise RuntimeError(name + " must be a float tensor")
+
+
+def check_int(t, name):
+    if t.dtype != torch.int32:
+        raise RuntimeError(name + " must be an int tensor")
+
+
+def check_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(name + " must be a CUDA tensor")
+
+
+def require_cuda_path(t):
+    """The reference raises "CPU not supported" for CPU inputs; so do we."""
+    if not t.is_cuda:
+        raise RuntimeError("CPU not supported")

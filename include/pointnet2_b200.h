@@ -1,0 +1,128 @@
+/*
+ * pointnet2_b200.h -- C ABI of lib3dvlp_b200.so, the B200 (sm_100a) implementation of 3DVLP's
+ * PointNet++ op suite and nn_distance.
+ *
+ * Boundary.  In the reference the Python layer (lib/pointnet2/pointnet2_utils.py:25-33) imports the
+ * pybind11 module `pointnet2._ext` (lib/pointnet2/_ext_src/src/bindings.cpp:11-24); inside it every
+ * op crosses a C-style launcher seam (raw device pointers + ints).  The functions below replace
+ * exactly those launchers, one for one, with three changes:
+ *   - the CUDA stream is an explicit argument (`stream`, a cudaStream_t passed as void*); the
+ *     reference reads at::cuda::getCurrentCUDAStream() inside every launcher;
+ *   - every function returns a status (0 = PN2_OK) and leaves a message for pn2_last_error();
+ *     the reference prints and calls exit(-1) on a failed launch (include/cuda_utils.h:35-44);
+ *   - no torch type appears in any signature.
+ * All pointers are DEVICE pointers on the current CUDA device; tensors are dense row-major fp32 /
+ * int32 exactly as the reference's CHECK_CONTIGUOUS / CHECK_IS_FLOAT / CHECK_IS_INT demand
+ * (include/utils.h:10-30).  Outputs are written by the callee and allocated by the caller; where the
+ * reference relies on a zero-filled output (ball_query.cpp:24-26, the *_grad outputs) this is noted.
+ * Calls are asynchronous on `stream`, stateless and re-entrant.
+ */
+#ifndef POINTNET2_B200_H_
+#define POINTNET2_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN2_OK 0
+#define PN2_ERR_INVALID 1 /* bad argument (shape, null pointer, unsupported size) */
+#define PN2_ERR_CUDA 2    /* a CUDA runtime call or kernel launch failed */
+
+/* Library identity / diagnostics. */
+int pn2_abi_version(void);
+const char* pn2_last_error(void);     /* thread-local; valid until the next failing call */
+int pn2_device_arch(int* major, int* minor); /* compute capability of the current device */
+
+/* ---------------------------------------------------------------------------------------------
+ * The nine launchers of pointnet2._ext
+ * ------------------------------------------------------------------------------------------- */
+
+/* furthest_point_sampling_kernel_wrapper(int b,int n,int m,const float* dataset,float* temp,int* idxs)
+ * -- src/sampling.cpp:16-18, kernel src/sampling_gpu.cu:75-178.
+ * dataset (b,n,3); idxs (b,m) int32.  Greedy FPS from index 0 with the reference's skip of points
+ * with |p|^2 <= 1e-3 and its thread/tree tie-break (bit-exact indices).  `temp` (b,n) is the
+ * reference's running-minimum scratch: this implementation keeps the minima on chip and never
+ * touches it (NULL is accepted).  m <= 0 returns PN2_OK without writing (sampling_gpu.cu:78). */
+int pn2_furthest_point_sampling(int b, int n, int m, const float* dataset, float* temp, int* idxs,
+                                void* stream);
+
+/* Same, fused with the gather that always follows it (pointnet2_modules.py:233-240): also writes
+ * new_xyz (b,m,3) = dataset[idxs].  new_xyz may be NULL. */
+int pn2_furthest_point_sampling_gather(int b, int n, int m, const float* dataset, int* idxs,
+                                       float* new_xyz, void* stream);
+
+/* gather_points_kernel_wrapper(int b,int c,int n,int npoints,const float* points,const int* idx,
+ * float* out) -- src/sampling.cpp:9-11, kernel sampling_gpu.cu:13-25.
+ * points (b,c,n), idx (b,npoints) -> out (b,c,npoints). */
+int pn2_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx,
+                      float* out, void* stream);
+
+/* gather_points_grad_kernel_wrapper -- src/sampling.cpp:12-14, kernel sampling_gpu.cu:39-52.
+ * grad_out (b,c,npoints), idx (b,npoints) -> grad_points (b,c,n) += ; caller zero-fills. */
+int pn2_gather_points_grad(int b, int c, int n, int npoints, const float* grad_out, const int* idx,
+                           float* grad_points, void* stream);
+
+/* query_ball_point_kernel_wrapper(int b,int n,int m,float radius,int nsample,const float* new_xyz,
+ * const float* xyz,int* idx) -- src/ball_query.cpp:9-11, kernel ball_query_gpu.cu:14-49.
+ * new_xyz (b,m,3), xyz (b,n,3) -> idx (b,m,nsample): the first nsample points (ascending index)
+ * with d2 < radius*radius, padded with the first hit; an empty ball yields zeros (this
+ * implementation writes them itself, no zero-fill needed). */
+int pn2_ball_query(int b, int n, int m, float radius, int nsample, const float* new_xyz,
+                   const float* xyz, int* idx, void* stream);
+
+/* group_points_kernel_wrapper(int b,int c,int n,int npoints,int nsample,const float* points,
+ * const int* idx,float* out) -- src/group_points.cpp:9-11, kernel group_points_gpu.cu:13-33.
+ * points (b,c,n), idx (b,npoints,nsample) -> out (b,c,npoints,nsample). */
+int pn2_group_points(int b, int c, int n, int npoints, int nsample, const float* points,
+                     const int* idx, float* out, void* stream);
+
+/* group_points_grad_kernel_wrapper -- src/group_points.cpp:13-15, kernel group_points_gpu.cu:48-69.
+ * grad_out (b,c,npoints,nsample) -> grad_points (b,c,n) += ; caller zero-fills. */
+int pn2_group_points_grad(int b, int c, int n, int npoints, int nsample, const float* grad_out,
+                          const int* idx, float* grad_points, void* stream);
+
+/* three_nn_kernel_wrapper(int b,int n,int m,const float* unknown,const float* known,float* dist2,
+ * int* idx) -- src/interpolate.cpp:9-11, kernel interpolate_gpu.cu:14-64.
+ * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3) SQUARED distances, idx (b,n,3) int32. */
+int pn2_three_nn(int b, int n, int m, const float* unknown, const float* known, float* dist2,
+                 int* idx, void* stream);
+
+/* three_interpolate_kernel_wrapper(int b,int c,int m,int n,const float* points,const int* idx,
+ * const float* weight,float* out) -- src/interpolate.cpp:12-13, kernel interpolate_gpu.cu:77-106.
+ * points (b,c,m), idx/weight (b,n,3) -> out (b,c,n). */
+int pn2_three_interpolate(int b, int c, int m, int n, const float* points, const int* idx,
+                          const float* weight, float* out, void* stream);
+
+/* three_interpolate_grad_kernel_wrapper(int b,int c,int n,int m,...) -- src/interpolate.cpp:14-17,
+ * kernel interpolate_gpu.cu:121-148.  grad_out (b,c,n) -> grad_points (b,c,m) += ; caller
+ * zero-fills.  NOTE: the reference BINDING (interpolate.cpp:95) launches the forward kernel by
+ * mistake; this is the scatter-add its kernel file intends. */
+int pn2_three_interpolate_grad(int b, int c, int n, int m, const float* grad_out, const int* idx,
+                               const float* weight, float* grad_points, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * nn_distance -- utils/nn_distance.py:32-59 (pure torch in the reference; one fused kernel here)
+ * ------------------------------------------------------------------------------------------- */
+#define PN2_NN_L2 0     /* sum (a-b)^2            (default)            */
+#define PN2_NN_L1 1     /* sum |a-b|              (l1=True)            */
+#define PN2_NN_HUBER 2  /* sum huber(a-b, delta)  (l1smooth=True)      */
+
+/* pc1 (b,n,c), pc2 (b,m,c) -> dist1 (b,n) f32, idx1 (b,n) i64, dist2 (b,m) f32, idx2 (b,m) i64.
+ * Ties keep the first index (torch.min). */
+int pn2_nn_distance(int b, int n, int m, int c, const float* pc1, const float* pc2, int mode,
+                    float delta, float* dist1, int64_t* idx1, float* dist2, int64_t* idx2,
+                    void* stream);
+
+/* Backward of the above w.r.t. pc1 and pc2 given grad_dist1 (b,n) / grad_dist2 (b,m) (either may
+ * be NULL) and the forward indices.  grad_pc1 (b,n,c) / grad_pc2 (b,m,c) += ; caller zero-fills. */
+int pn2_nn_distance_grad(int b, int n, int m, int c, const float* pc1, const float* pc2, int mode,
+                         float delta, const int64_t* idx1, const int64_t* idx2,
+                         const float* grad_dist1, const float* grad_dist2, float* grad_pc1,
+                         float* grad_pc2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POINTNET2_B200_H_ */
