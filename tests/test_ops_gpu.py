@@ -129,7 +129,9 @@ def test_three_nn_bit_exact(pkg, oracle, cuda, n, m):
     assert torch.equal(ig.cpu(), iw)
     assert torch.equal(d2g.cpu(), d2w)  # +inf in unfilled slots compares equal
     dist, idx = pkg.pointnet2_utils.three_nn(u.to(cuda), k.to(cuda))
-    assert torch.equal(dist.cpu(), torch.sqrt(d2w))
+    # the Python wrapper applies torch.sqrt on the device, like pointnet2_utils.py:138-140
+    torch.testing.assert_close(dist.cpu(), torch.sqrt(d2w), rtol=1e-6, atol=0)
+    assert torch.equal(idx, ig)
 
 
 @pytest.mark.parametrize("c", [1, 256])
