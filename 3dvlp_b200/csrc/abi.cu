@@ -31,7 +31,34 @@ int sm_count() {
   return cached[dev];
 }
 
+// One int per device, set by a kernel whose bounded mbarrier wait timed out (a protocol bug must
+// surface as an error, never as a hung GPU).  Polled by pn2_poll_device_error().
+static int* g_err_flag[64] = {nullptr};
+
+int* device_err_flag() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!g_err_flag[dev]) {
+    int* p = nullptr;
+    if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, sizeof(int));
+    g_err_flag[dev] = p;
+  }
+  return g_err_flag[dev];
+}
+
 }  // namespace pn2
+
+extern "C" int pn2_poll_device_error(int* flag_out, void* stream) {
+  int* p = pn2::device_err_flag();
+  if (!p) { pn2::set_error("poll_device_error: no flag"); return PN2_ERR_CUDA; }
+  int v = 0;
+  PN2_CUDA(cudaMemcpyAsync(&v, p, sizeof(int), cudaMemcpyDeviceToHost, pn2::as_stream(stream)));
+  PN2_CUDA(cudaStreamSynchronize(pn2::as_stream(stream)));
+  if (v != 0) PN2_CUDA(cudaMemsetAsync(p, 0, sizeof(int), pn2::as_stream(stream)));
+  if (flag_out) *flag_out = v;
+  return PN2_OK;
+}
 
 extern "C" int pn2_abi_version(void) { return 1; }
 

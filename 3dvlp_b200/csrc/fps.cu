@@ -251,21 +251,9 @@ int dispatch_p(int p, const FpsArgs& a, int b, cudaStream_t s) {
   return PN2_ERR_INVALID;
 }
 
-int* g_err_flag[64] = {nullptr};  // one device flag per device ordinal
-
-int* err_flag() {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (!g_err_flag[dev]) {
-    int* p = nullptr;
-    if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(p, 0, sizeof(int));
-    g_err_flag[dev] = p;
-  }
-  return g_err_flag[dev];
-}
-
 }  // namespace
+
+int* device_err_flag();  // abi.cu
 
 // Tunables (read once): PN2_FPS_CLUSTER = 1 | 8 | 16, PN2_FPS_THREADS = 512 | 1024.
 static int env_int(const char* name, int dflt) {
@@ -283,7 +271,7 @@ int fps_run(int b, int n, int m, const float* dataset, int* idxs, float* new_xyz
   FpsArgs a;
   a.xyz = dataset; a.idxs = idxs; a.new_xyz = new_xyz;
   a.n = n; a.m = m; a.log2bs = log2bs; a.rows = (n + bs - 1) / bs;
-  a.err = err_flag();
+  a.err = device_err_flag();
   PN2_REQUIRE(a.err != nullptr, "furthest_point_sampling: cannot allocate the device error flag");
 
   static const int force_cluster = env_int("PN2_FPS_CLUSTER", 0);

@@ -34,6 +34,9 @@ extern "C" {
 int pn2_abi_version(void);
 const char* pn2_last_error(void);     /* thread-local; valid until the next failing call */
 int pn2_device_arch(int* major, int* minor); /* compute capability of the current device */
+/* Synchronises `stream` and reads (then clears) the device-side protocol error flag: 0 = none,
+ * 1 = FPS cluster exchange timed out, 2 = tensor-core pipeline timed out.  Debug aid. */
+int pn2_poll_device_error(int* flag_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The nine launchers of pointnet2._ext
@@ -121,6 +124,25 @@ int pn2_nn_distance_grad(int b, int n, int m, int c, const float* pc1, const flo
                          float delta, const int64_t* idx1, const int64_t* idx2,
                          const float* grad_dist1, const float* grad_dist2, float* grad_pc1,
                          float* grad_pc2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SharedMLP on tcgen05 tensor cores -- pytorch_utils.py:11-36 (Conv2d 1x1 -> BatchNorm2d -> ReLU;
+ * cuDNN in the reference).  BatchNorm (eval) is folded into W / bias by the host layer.
+ * ------------------------------------------------------------------------------------------- */
+
+/* W (n,k) fp32 row-major -> bf16, K zero-padded to kpad (multiple of 64), in the tile layout the
+ * kernels below consume: kpad/64 panels of n rows x 128 bytes, SWIZZLE_128B.  out: n*kpad*2 bytes. */
+int pn2_pack_weight_bf16(int n, int k, int kpad, const float* w, void* out, void* stream);
+
+/* features (b,c,n) fp32 channel-major (the reference's feature layout) -> (b*n, kpad) bf16 rows. */
+int pn2_pack_rows_bf16(int b, int c, int n, int kpad, const float* features, void* out, void* stream);
+
+/* Y = act(X W^T + bias).  X (m,k) bf16 row-major, k % 64 == 0; W packed as above (n % 16 == 0,
+ * n <= 256); bias (n) fp32 or NULL; relu 0/1.  out_mode 0: Y fp32 (m,n) row-major; 1: Y bf16 (m,n)
+ * row-major; 2: Y fp32 channel-major (m / rows_per_batch, n, rows_per_batch) -- the reference's
+ * (B, C, npoint) feature layout. */
+int pn2_linear_bf16(int m, int n, int k, const void* x_bf16, const void* w_packed, const float* bias,
+                    int relu, int out_mode, int rows_per_batch, void* y, void* stream);
 
 #ifdef __cplusplus
 }
