@@ -117,6 +117,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug must surface as an error flag, never as a hung GPU box.
 // Returns false after ~2^26 polls (seconds) so the caller can bail out.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 26); ++it) {
     if (mbar_try_wait(bar, parity)) return true;
   }

@@ -1,5 +1,6 @@
 // Furthest point sampling for sm_100a: one thread-block CLUSTER per scene, every point resident in
-// registers for the whole run, one associative packed-key arg-max per round.
+// registers for the whole run, one associative packed-key arg-max per round, and SEVERAL samples
+// accepted per round.
 //
 // Replaces furthest_point_sampling_kernel (reference lib/pointnet2/_ext_src/src/sampling_gpu.cu:75-178),
 // which runs ONE 512-thread CTA per scene and re-reads xyz and the running minima from global
@@ -19,23 +20,40 @@
 // between threads the packed key decides.  For a fixed row, consecutive tid read consecutive k
 // (coalesced one-time load).
 //
-// Per round: P distance updates per thread (registers only) -> redux.sync max/min inside the warp ->
-// one __syncthreads -> warp 0 reduces the warp records and posts the CTA's candidate {value, key,
-// x, y, z} into every peer's shared memory with st.async (DSMEM store that completes a transaction
-// on the peer's mbarrier) -> every CTA waits on its own mbarrier and reduces the CLUSTER
-// candidates redundantly, so all CTAs know the new centre's coordinates without touching global
-// memory.  There is no cluster-wide barrier inside the loop.
+// Batched acceptance (what makes the serial chain short).  The reduction keeps, per group (lane,
+// warp, CTA), the best point AND the value of the best point it did NOT report ("second").  After
+// one exchange every CTA holds G candidates -- one per CTA of the cluster (or one per warp in the
+// single-CTA kernel) -- and  bound = max of the groups' seconds  dominates every point that is not a
+// candidate.  Running minima only decrease, so warp 0 can replay greedy FPS on the G candidates
+// alone: accept the arg-max, lower the other candidates by their exact distance to it (same fp32
+// expression as the bulk update), and accept the next arg-max as long as its value stays strictly
+// above `bound` and above zero -- then it is provably the point the reference would pick next.  The
+// accepted centres (up to KMAX per round) are applied to all points in the next bulk update.  On
+// ScanNet-like scenes ~3-5 samples are accepted per exchange, so the number of dependent
+// exchange rounds drops from m-1 to roughly (m-1)/4 with bit-identical output.
+//
+// Per round: K x P distance updates per thread (registers only) -> redux.sync inside the warp ->
+// __syncthreads -> warp 0 reduces the warp records and posts the CTA's candidate into every peer's
+// shared memory with st.async (DSMEM store completing a transaction on the peer's mbarrier) ->
+// warp 0 waits on its own mbarrier, runs the acceptance loop, publishes the new centres ->
+// __syncthreads.  There is no cluster-wide barrier inside the loop.
 #include "common.cuh"
 
 namespace pn2 {
+#ifndef PN2_FPS_TIMING
 namespace {
+#endif
+
+constexpr int KMAX = 8;      // samples accepted per exchange round at most
+constexpr int MAXC = 16;     // largest cluster
 
 struct FpsArgs {
   const float* xyz;  // (b, n, 3)
   int* idxs;         // (b, m)
   float* new_xyz;    // (b, m, 3) or nullptr
   int* err;          // device error flag (protocol time-out)
-  int n, m, log2bs, rows;
+  int n, m, log2bs, rows, csize;
+  long long* dbg;    // PN2_FPS_TIMING builds only
 };
 
 __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c,
@@ -45,14 +63,16 @@ __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t a, uint32_t
       ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar)
       : "memory");
 }
-__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t a, uint32_t rbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr),
-               "r"(a), "r"(rbar)
+__device__ __forceinline__ void st_async_v2(uint32_t raddr, uint32_t a, uint32_t b, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(
+                   raddr),
+               "r"(a), "r"(b), "r"(rbar)
                : "memory");
 }
 
-// Reduce NR (<= 32) records held one per lane (lanes >= NR pass INT_MIN / ~0u): returns the lane
-// that holds the arg-max of (value, -key); value/key of the winner are returned by reference.
+// arg-max of (value, -key) over the lanes of a warp; lanes without a record pass v = INT_MIN.
+// Returns the source lane; v / k become the winner's.  Value ties fall back to the keys, which
+// are unique.
 __device__ __forceinline__ int warp_argmax(int& v, uint32_t& k) {
   const int vmax = __reduce_max_sync(0xffffffffu, v);
   const uint32_t kk = (v == vmax) ? k : 0xffffffffu;
@@ -63,26 +83,36 @@ __device__ __forceinline__ int warp_argmax(int& v, uint32_t& k) {
   return __ffs(win) - 1;
 }
 
-template <int P, int THREADS, int CLUSTER>
+struct Centres {          // published by warp 0 each round
+  float4 c[KMAX];         // accepted centres (x, y, z, -)
+  int count;
+};
+
+template <int P, int THREADS, bool CLUSTERED>
 __global__ void __launch_bounds__(THREADS, 1) fps_kernel(const FpsArgs a) {
   constexpr int NW = THREADS / 32;
-  constexpr int NC = CLUSTER > 1 ? CLUSTER : 1;
-  __shared__ uint2 w_vk[2][NW];
-  __shared__ float4 w_xyz[2][NW];
-  __shared__ __align__(16) uint4 cand[2][NC];  // {value bits, key32, x, y}
-  __shared__ float cand_z[2][NC];
+  __shared__ uint2 w_vk[NW];                      // warp record: value bits, key
+  __shared__ float4 w_xyz[NW];                    // x, y, z, second
+  __shared__ __align__(16) uint4 cand[2][MAXC];   // {value bits, key32, x, y}
+  __shared__ __align__(8) uint2 cand_zs[2][MAXC]; // {z, second}
   __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ Centres ctr;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t rank = CLUSTER > 1 ? cluster_ctarank() : 0u;
-  const int scene = blockIdx.x / CLUSTER;
+  const int csize = CLUSTERED ? a.csize : 1;
+  const uint32_t rank = CLUSTERED ? cluster_ctarank() : 0u;
+  const int scene = blockIdx.x / csize;
   const int n = a.n, m = a.m, log2bs = a.log2bs;
   const float* __restrict__ xyz = a.xyz + static_cast<size_t>(scene) * n * 3;
   int* __restrict__ idxs = a.idxs + static_cast<size_t>(scene) * m;
   float* __restrict__ oxyz = a.new_xyz ? a.new_xyz + static_cast<size_t>(scene) * m * 3 : nullptr;
 
   const uint32_t bsmask = (1u << log2bs) - 1u;
-  const uint32_t g = rank * THREADS + tid;
+  // Thread -> reference-thread map: consecutive reference threads (consecutive point indices) are
+  // dealt to DIFFERENT warps, so that when the input is already in sampling order (SA2..SA4 run FPS
+  // on the previous layer's FPS output, whose next samples are k, k+1, k+2, ...) the per-warp
+  // candidates of one round are distinct upcoming samples and the batch acceptance stays long.
+  const uint32_t g = rank * THREADS + static_cast<uint32_t>(lane) * NW + warp;
   const uint32_t v = g & bsmask;
   const uint32_t seg = g >> log2bs;
   const uint32_t rowmask = log2bs ? ((1u << (32 - log2bs)) - 1u) : 0xffffffffu;
@@ -105,160 +135,260 @@ __global__ void __launch_bounds__(THREADS, 1) fps_kernel(const FpsArgs a) {
     }
   }
   const float x0 = __ldg(xyz), y0 = __ldg(xyz + 1), z0 = __ldg(xyz + 2);
-  float ox = x0, oy = y0, oz = z0;
 
-  if (CLUSTER > 1) {
-    if (tid == 0) {
+  if (tid == 0) {
+    if (CLUSTERED) {
       mbar_init(&mbar[0], 1);
       mbar_init(&mbar[1], 1);
       fence_mbar_init_cluster();
     }
-    cluster_sync_all();
+    ctr.c[0] = make_float4(x0, y0, z0, 0.f);  // sample 0 is index 0 (sampling_gpu.cu:89-90)
+    ctr.count = 1;
+    if (rank == 0) {
+      idxs[0] = 0;
+      if (oxyz) { oxyz[0] = x0; oxyz[1] = y0; oxyz[2] = z0; }
+    }
   }
-  if (rank == 0 && tid == 0) {
-    idxs[0] = 0;
-    if (oxyz) { oxyz[0] = x0; oxyz[1] = y0; oxyz[2] = z0; }
-  }
+  if (CLUSTERED) cluster_sync_all(); else __syncthreads();
 
-  for (int j = 1; j < m; ++j) {
-    const int par = j & 1;
-    if (CLUSTER > 1 && tid == 0) mbar_arrive_expect_tx(&mbar[par], CLUSTER * 20u);
+#ifdef PN2_FPS_TIMING
+  long long tacc[6] = {0, 0, 0, 0, 0, 0};
+  long long nrounds = 0;
+#define PN2_T(i) { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; }
+  long long tprev = clock64();
+#else
+#define PN2_T(i)
+#endif
 
-    // ---- A: update the running minima of the owned points, thread-local arg-max -------------
-    float best = -1.f;
+  int j = 1;            // samples emitted so far
+  uint32_t round = 0;   // exchange rounds done (mbarrier parity bookkeeping)
+  while (j < m) {
+    const uint32_t par = round & 1u;
+    if (CLUSTERED && tid == 0) mbar_arrive_expect_tx(&mbar[par], static_cast<uint32_t>(csize) * 24u);
+
+    // ---- A: apply the centres accepted last round; thread-local best and second --------------
+    const int kc = ctr.count;
+    for (int c = 0; c < kc; ++c) {
+      const float4 o = ctr.c[c];
+#pragma unroll
+      for (int i = 0; i < P; ++i)
+        pt[i] = fminf(sqdist3(px[i] - o.x, py[i] - o.y, pz[i] - o.z), pt[i]);
+    }
+    float best = -1.f, second = -1.f;
     int bslot = 0;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      const float d = sqdist3(px[i] - ox, py[i] - oy, pz[i] - oz);
-      const float t = fminf(d, pt[i]);
-      pt[i] = t;
-      if (t > best) { best = t; bslot = i; }
+      const float t = pt[i];
+      if (t > best) { second = best; best = t; bslot = i; }
+      else second = fmaxf(second, t);
     }
-    // ---- B: warp arg-max with two redux.sync ---------------------------------------------------
-    int vb = __float_as_int(best);  // best >= 0 or exactly -1.0f: signed-int order == float order
-    uint32_t key = keybase + bslot;
+    PN2_T(0)
+    // all threads have read ctr (count + centres) before warp 0 may overwrite it below
+    // (ordering is provided by the __syncthreads that follows phase B)
+    // ---- B: warp record = arg-max + best value among everything else in the warp -------------
     {
+      const int vb = __float_as_int(best);  // best >= 0 or exactly -1.0f: int order == float order
+      const uint32_t key = keybase + bslot;
       const int vmax = __reduce_max_sync(0xffffffffu, vb);
       const uint32_t kk = (vb == vmax) ? key : 0xffffffffu;
       const uint32_t kmin = __reduce_min_sync(0xffffffffu, kk);
-      if (kk == kmin) {  // exactly one lane: keys are unique
+      const bool win = (kk == kmin);  // exactly one lane: keys are unique
+      const int sec = __reduce_max_sync(0xffffffffu, __float_as_int(win ? second : best));
+      if (win) {
         float bx = px[0], by = py[0], bz = pz[0];
 #pragma unroll
         for (int i = 1; i < P; ++i)
           if (bslot == i) { bx = px[i]; by = py[i]; bz = pz[i]; }
-        w_vk[par][warp] = make_uint2(static_cast<uint32_t>(vmax), kmin);
-        w_xyz[par][warp] = make_float4(bx, by, bz, 0.f);
+        w_vk[warp] = make_uint2(static_cast<uint32_t>(vmax), kmin);
+        w_xyz[warp] = make_float4(bx, by, bz, __int_as_float(sec));
       }
     }
+    PN2_T(1)
     __syncthreads();
+    PN2_T(2)
 
-    int gv;
-    uint32_t gk;
-    float gx, gy, gz;
-    if (CLUSTER == 1) {
-      // ---- C: every warp reduces the NW warp records redundantly (no second barrier) ---------
-      int rv = INT_MIN;
-      uint32_t rk = 0xffffffffu;
-      if (lane < NW) { const uint2 r = w_vk[par][lane]; rv = static_cast<int>(r.x); rk = r.y; }
-      const int src = warp_argmax(rv, rk);
-      const float4 w = w_xyz[par][src];
-      gv = rv; gk = rk; gx = w.x; gy = w.y; gz = w.z;
-    } else {
-      // ---- C+D: warp 0 reduces the CTA and posts its candidate to all peers -------------------
-      if (warp == 0) {
-        int rv = INT_MIN;
-        uint32_t rk = 0xffffffffu;
-        if (lane < NW) { const uint2 r = w_vk[par][lane]; rv = static_cast<int>(r.x); rk = r.y; }
+    if (warp == 0) {
+      // candidate list of this warp: one record per lane
+      int cv = INT_MIN;                // value bits (INT_MIN = no record)
+      uint32_t ck = 0xffffffffu;
+      float cx = 0.f, cy = 0.f, cz = 0.f;
+      int csec = INT_MIN;
+      bool ok = true;
+      if (lane < NW) {
+        const uint2 r = w_vk[lane];
+        const float4 w = w_xyz[lane];
+        cv = static_cast<int>(r.x); ck = r.y; cx = w.x; cy = w.y; cz = w.z; csec = __float_as_int(w.w);
+      }
+      if (CLUSTERED) {
+        // ---- C+D: reduce the CTA, post {best, second} to every peer ---------------------------
+        int rv = cv;
+        uint32_t rk = ck;
         const int src = warp_argmax(rv, rk);
-        const float4 w = w_xyz[par][src];
-        if (lane < CLUSTER) {
+        const int cta_sec = __reduce_max_sync(0xffffffffu, lane == src ? csec : cv);
+        const float sx = __shfl_sync(0xffffffffu, cx, src), sy = __shfl_sync(0xffffffffu, cy, src),
+                    sz = __shfl_sync(0xffffffffu, cz, src);
+        if (lane < csize) {
           const uint32_t rbar = mapa_u32(smem_u32(&mbar[par]), lane);
           st_async_v4(mapa_u32(smem_u32(&cand[par][rank]), lane), static_cast<uint32_t>(rv), rk,
-                      __float_as_uint(w.x), __float_as_uint(w.y), rbar);
-          st_async_b32(mapa_u32(smem_u32(&cand_z[par][rank]), lane), __float_as_uint(w.z), rbar);
+                      __float_as_uint(sx), __float_as_uint(sy), rbar);
+          st_async_v2(mapa_u32(smem_u32(&cand_zs[par][rank]), lane), __float_as_uint(sz),
+                      static_cast<uint32_t>(cta_sec), rbar);
+        }
+        PN2_T(3)
+        ok = mbar_wait(&mbar[par], (round >> 1) & 1u);
+        PN2_T(4)
+        cv = INT_MIN; ck = 0xffffffffu; csec = INT_MIN;
+        if (ok && lane < csize) {
+          const uint4 c = cand[par][lane];
+          const uint2 zs = cand_zs[par][lane];
+          cv = static_cast<int>(c.x); ck = c.y; cx = __uint_as_float(c.z); cy = __uint_as_float(c.w);
+          cz = __uint_as_float(zs.x); csec = static_cast<int>(zs.y);
         }
       }
-      // ---- E: wait for the CLUSTER candidates, reduce them redundantly in every warp ----------
-      if (!mbar_wait(&mbar[par], ((j - 1) >> 1) & 1)) {
-        if (tid == 0) atomicExch(a.err, 1);
-        break;
+      // ---- E: greedy acceptance on the candidates (exact, see header) --------------------------
+      // Warp 0 is alone on the critical path here, so the loop carries only what the next
+      // iteration needs: arg-max, broadcast of the winner's xyz, the candidates' update.  Lane k
+      // keeps the k-th accepted record; decoding, the shared-memory publish and the global stores
+      // happen once after the loop, one lane per sample.
+      const int bound = __reduce_max_sync(0xffffffffu, csec);
+      const int room = min(KMAX, m - j);
+      int k = 0;
+      uint32_t mykey = 0;
+      int myval = -1;
+      float mx = x0, my = y0, mz = z0;
+      while (ok) {
+        const int rv = __reduce_max_sync(0xffffffffu, cv);
+        if (k > 0 && !(rv > bound && rv > 0)) break;  // int compare == float compare for values >= 0
+        uint32_t tie = __ballot_sync(0xffffffffu, cv == rv);
+        if (__popc(tie) > 1) {  // equal values: the smallest key wins (keys are unique)
+          const uint32_t kk = (cv == rv) ? ck : 0xffffffffu;
+          const uint32_t kmin = __reduce_min_sync(0xffffffffu, kk);
+          tie = __ballot_sync(0xffffffffu, kk == kmin);
+        }
+        const int src = __ffs(tie) - 1;
+        const float ax = __shfl_sync(0xffffffffu, cx, src), ay = __shfl_sync(0xffffffffu, cy, src),
+                    az = __shfl_sync(0xffffffffu, cz, src);
+        const uint32_t ak = __shfl_sync(0xffffffffu, ck, src);
+        if (lane == k) { mykey = ak; myval = rv; mx = ax; my = ay; mz = az; }
+        ++k;
+        if (k >= room || rv < 0) break;
+        // lower every candidate -- the accepted one included -- by its exact distance to the new
+        // centre: a finite point drops to 0 and can never be re-accepted in this round (rv > 0); a
+        // point with inf/NaN coordinates keeps its value (d is NaN) exactly as in the reference
+        if (cv >= 0) cv = __float_as_int(fminf(sqdist3(cx - ax, cy - ay, cz - az), __int_as_float(cv)));
       }
-      int rv = INT_MIN;
-      uint32_t rk = 0xffffffffu;
-      if (lane < CLUSTER) { const uint4 c = cand[par][lane]; rv = static_cast<int>(c.x); rk = c.y; }
-      const int src = warp_argmax(rv, rk);
-      const uint4 c = cand[par][src];
-      gv = rv; gk = rk; gx = __uint_as_float(c.z); gy = __uint_as_float(c.w); gz = cand_z[par][src];
+      if (ok && lane < k) {
+        int old = 0;
+        if (myval < 0) {  // no eligible point anywhere: every reference thread reports besti = 0
+          mx = x0; my = y0; mz = z0;
+        } else {
+          const uint32_t row = mykey & rowmask;
+          const uint32_t vv = log2bs ? __brev(mykey & ~rowmask) : 0u;
+          old = static_cast<int>(vv + (row << log2bs));
+        }
+        ctr.c[lane] = make_float4(mx, my, mz, 0.f);
+        if (rank == 0) {
+          idxs[j + lane] = old;
+          if (oxyz) { oxyz[3 * (j + lane)] = mx; oxyz[3 * (j + lane) + 1] = my; oxyz[3 * (j + lane) + 2] = mz; }
+        }
+      }
+      if (lane == 0) ctr.count = ok ? k : -1;
     }
-
-    int old;
-    if (gv < 0) {  // no eligible point at all: every reference thread reports besti = 0
-      old = 0; ox = x0; oy = y0; oz = z0;
-    } else {
-      const uint32_t row = gk & rowmask;
-      const uint32_t vv = log2bs ? __brev(gk & ~rowmask) : 0u;
-      old = static_cast<int>(vv + (row << log2bs));
-      ox = gx; oy = gy; oz = gz;
+    __syncthreads();
+    const int got = ctr.count;
+    if (got < 0) {
+      if (tid == 0) atomicExch(a.err, 1);
+      break;
     }
-    if (rank == 0 && tid == 0) {
-      idxs[j] = old;
-      if (oxyz) { oxyz[3 * j] = ox; oxyz[3 * j + 1] = oy; oxyz[3 * j + 2] = oz; }
-    }
+    j += got;
+    ++round;
+    PN2_T(5)
+#ifdef PN2_FPS_TIMING
+    ++nrounds;
+#endif
   }
+#ifdef PN2_FPS_TIMING
+  if (blockIdx.x == 0 && tid == 0 && a.dbg) {
+    for (int i = 0; i < 6; ++i) a.dbg[i] = tacc[i];
+    a.dbg[6] = nrounds;
+  }
+#endif
   // peers may still be storing into this CTA's shared memory: leave together
-  if (CLUSTER > 1) cluster_sync_all();
+  if (CLUSTERED) cluster_sync_all();
 }
 
-template <int P, int THREADS, int CLUSTER>
-int launch(const FpsArgs& a, int b, cudaStream_t stream) {
-  auto kern = fps_kernel<P, THREADS, CLUSTER>;
+template <int P, int THREADS, bool CLUSTERED>
+int launch(const FpsArgs& a, int b, cudaStream_t stream, int* max_active) {
+  auto kern = fps_kernel<P, THREADS, CLUSTERED>;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(b) * CLUSTER);
+  cfg.gridDim = dim3(static_cast<unsigned>(b) * (CLUSTERED ? a.csize : 1));
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   int nattr = 0;
-  if (CLUSTER > 1) {
-    if (CLUSTER > 8) PN2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  if (CLUSTERED) {
+    if (a.csize > 8) PN2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.x = a.csize;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     nattr = 1;
   }
   cfg.attrs = attr;
   cfg.numAttrs = nattr;
+  if (max_active) {  // occupancy probe only
+    PN2_CUDA(cudaOccupancyMaxActiveClusters(max_active, kern, &cfg));
+    return PN2_OK;
+  }
   PN2_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   return PN2_OK;
 }
 
-template <int THREADS, int CLUSTER>
-int dispatch_p(int p, const FpsArgs& a, int b, cudaStream_t s) {
+template <int THREADS, bool CLUSTERED>
+int dispatch_p(int p, const FpsArgs& a, int b, cudaStream_t s, int* max_active) {
   switch (p) {
-    case 1: return launch<1, THREADS, CLUSTER>(a, b, s);
-    case 2: return launch<2, THREADS, CLUSTER>(a, b, s);
-    case 3: return launch<3, THREADS, CLUSTER>(a, b, s);
-    case 4: return launch<4, THREADS, CLUSTER>(a, b, s);
-    case 5: return launch<5, THREADS, CLUSTER>(a, b, s);
-    case 6: return launch<6, THREADS, CLUSTER>(a, b, s);
-    case 7: case 8: return launch<8, THREADS, CLUSTER>(a, b, s);
-    case 9: case 10: case 11: case 12: return launch<12, THREADS, CLUSTER>(a, b, s);
-    case 13: case 14: case 15: case 16: return launch<16, THREADS, CLUSTER>(a, b, s);
+    case 1: return launch<1, THREADS, CLUSTERED>(a, b, s, max_active);
+    case 2: return launch<2, THREADS, CLUSTERED>(a, b, s, max_active);
+    case 3: return launch<3, THREADS, CLUSTERED>(a, b, s, max_active);
+    case 4: return launch<4, THREADS, CLUSTERED>(a, b, s, max_active);
+    case 5: return launch<5, THREADS, CLUSTERED>(a, b, s, max_active);
+    case 6: return launch<6, THREADS, CLUSTERED>(a, b, s, max_active);
+    case 7: case 8: return launch<8, THREADS, CLUSTERED>(a, b, s, max_active);
+    case 9: case 10: return launch<10, THREADS, CLUSTERED>(a, b, s, max_active);
+    case 11: case 12: return launch<12, THREADS, CLUSTERED>(a, b, s, max_active);
+    case 13: case 14: case 15: case 16: return launch<16, THREADS, CLUSTERED>(a, b, s, max_active);
     default: break;
   }
   set_error("furthest_point_sampling: n too large for the register-resident kernel (P=%d)", p);
   return PN2_ERR_INVALID;
 }
 
+#ifndef PN2_FPS_TIMING
 }  // namespace
+#endif
 
 int* device_err_flag();  // abi.cu
+#ifdef PN2_FPS_TIMING
+long long* fps_dbg_ptr = nullptr;
+#endif
 
-// Tunables (read once): PN2_FPS_CLUSTER = 1 | 8 | 16, PN2_FPS_THREADS = 512 | 1024.
+// Tunables (read once): PN2_FPS_CLUSTER = 1 | 2..16, PN2_FPS_THREADS = 512 | 1024.
 static int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
+}
+
+static int run_cfg(int cluster, int threads, FpsArgs a, int bs, int b, cudaStream_t stream, int* max_active) {
+  a.csize = cluster;
+  const int segs = cluster * threads / bs;  // >= 1: threads >= 512 >= bs
+  const int p = (a.rows + segs - 1) / segs;
+  if (cluster == 1) {
+    if (threads == 512) return dispatch_p<512, false>(p, a, b, stream, max_active);
+    return dispatch_p<1024, false>(p, a, b, stream, max_active);
+  }
+  if (threads == 512) return dispatch_p<512, true>(p, a, b, stream, max_active);
+  return dispatch_p<1024, true>(p, a, b, stream, max_active);
 }
 
 int fps_run(int b, int n, int m, const float* dataset, int* idxs, float* new_xyz, cudaStream_t stream) {
@@ -270,28 +400,56 @@ int fps_run(int b, int n, int m, const float* dataset, int* idxs, float* new_xyz
   while ((1 << log2bs) < bs) ++log2bs;
   FpsArgs a;
   a.xyz = dataset; a.idxs = idxs; a.new_xyz = new_xyz;
-  a.n = n; a.m = m; a.log2bs = log2bs; a.rows = (n + bs - 1) / bs;
+  a.n = n; a.m = m; a.log2bs = log2bs; a.rows = (n + bs - 1) / bs; a.csize = 1;
   a.err = device_err_flag();
+  a.dbg = nullptr;
+#ifdef PN2_FPS_TIMING
+  if (!fps_dbg_ptr) cudaMalloc(&fps_dbg_ptr, 8 * sizeof(long long));
+  a.dbg = fps_dbg_ptr;
+#endif
   PN2_REQUIRE(a.err != nullptr, "furthest_point_sampling: cannot allocate the device error flag");
 
   static const int force_cluster = env_int("PN2_FPS_CLUSTER", 0);
   static const int force_threads = env_int("PN2_FPS_THREADS", 0);
-  int cluster = force_cluster ? force_cluster : (n > 8192 ? 16 : 1);
-  int threads = force_threads ? force_threads : (cluster == 1 ? (n <= 512 ? 512 : 1024) : 512);
-  if (cluster == 16 && threads == 512 && a.rows > 16 * 16) threads = 1024;
-  const int segs = cluster * threads / bs;  // >= 1: threads >= 512 >= bs
-  const int p = (a.rows + segs - 1) / segs;
-  if (cluster == 1 && threads == 512) return dispatch_p<512, 1>(p, a, b, stream);
-  if (cluster == 1) return dispatch_p<1024, 1>(p, a, b, stream);
-  if (cluster == 8 && threads == 512) return dispatch_p<512, 8>(p, a, b, stream);
-  if (cluster == 8) return dispatch_p<1024, 8>(p, a, b, stream);
-  if (cluster == 16 && threads == 512) return dispatch_p<512, 16>(p, a, b, stream);
-  if (cluster == 16) return dispatch_p<1024, 16>(p, a, b, stream);
-  set_error("furthest_point_sampling: unsupported PN2_FPS_CLUSTER=%d", cluster);
-  return PN2_ERR_INVALID;
+  int cluster, threads;
+  if (force_cluster) {
+    cluster = force_cluster;
+    threads = force_threads ? force_threads : 512;
+  } else if (n <= 8192) {
+    cluster = 1;
+    threads = force_threads ? force_threads : (n <= 2048 ? 512 : 1024);
+  } else {
+    // The largest cluster whose co-resident count covers the whole batch in ONE wave (a B200 GPC
+    // holds a single 16-CTA cluster and one GPC is short of 16 SMs: 7 such clusters fit, 15 of 8).
+    threads = force_threads ? force_threads : 512;
+    static int active_cache[MAXC + 1] = {0};
+    cluster = 8;
+    for (int cs = 16; cs >= 8; cs -= 2) {
+      if (a.rows > cs * (threads / bs) * 16) continue;  // would not fit the register budget
+      if (!active_cache[cs]) {
+        int act = 0;
+        if (run_cfg(cs, threads, a, bs, b, stream, &act) != PN2_OK || act <= 0) act = -1;
+        active_cache[cs] = act;
+      }
+      if (active_cache[cs] >= b) { cluster = cs; break; }
+    }
+    if (a.rows > cluster * (threads / bs) * 16) { cluster = 16; threads = 1024; }
+  }
+  PN2_REQUIRE(cluster >= 1 && cluster <= MAXC && (threads == 512 || threads == 1024),
+              "furthest_point_sampling: unsupported cluster=%d threads=%d", cluster, threads);
+  return run_cfg(cluster, threads, a, bs, b, stream, nullptr);
 }
 
 }  // namespace pn2
+
+#ifdef PN2_FPS_TIMING
+// developer build only (tools/fps_timing.py): per-phase cycle sums + round count of the last launch
+extern "C" int pn2_fps_timing(long long* out7) {
+  if (!pn2::fps_dbg_ptr) return 1;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(out7, pn2::fps_dbg_ptr, 7 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess;
+}
+#endif
 
 extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float* dataset, float* temp,
                                            int* idxs, void* stream) {

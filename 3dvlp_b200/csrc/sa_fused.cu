@@ -1,0 +1,325 @@
+// Fused set-abstraction body: grouping + shared MLP (3 layers) + max-pool in ONE kernel (sm_100a).
+//
+// Reference path (pointnet2_modules.py:243-257): QueryAndGroup materialises the grouped tensor
+// (B, 3+C, npoint, nsample) in HBM (group_points_gpu.cu:13-33, 70.8 MB/scene for SA1 at 135
+// channels), then three cuDNN 1x1 convolutions + BatchNorm + ReLU read and write (B, C, npoint,
+// nsample) activations, then max_pool2d.  Here nothing but the pooled (B, C3, npoint) result leaves
+// the SM:
+//
+//   layer 1  is split algebraically.  A 1x1 convolution commutes with the neighbourhood gather, so
+//            the feature half  W1[:,3:] . f  is evaluated once per INPUT point (pn2_linear_bf16 ->
+//            `g`, or directly from <= 4 raw channels) and only gathered here; the geometric half
+//            W1[:,0:3] . (p - centre)/radius  is three FMAs per channel in fp32.  One warp builds
+//            32 rows of the 128-row tile: lane = channels, rows broadcast by shuffle, the row of g
+//            is read coalesced, weights stay in registers.  Result -> ReLU -> bf16 -> shared memory
+//            in the SWIZZLE_128B K-major operand layout.
+//   layer 2  D2[128 rows x C2] = X1 . W2^T   tcgen05.mma, rows on the TMEM lanes; the epilogue
+//            (thread = row) adds bias, ReLU, rounds to bf16 and overwrites the tile as X2.
+//   layer 3  transposed: D3[C3 channels x 128 rows] = W3 . X2^T, i.e. the weights are the A operand
+//            and the activation tile the B operand (both K-major, same shared-memory image), so
+//            output channels land on TMEM lanes and the nsample neighbours of a centre are
+//            consecutive TMEM columns: max-pooling is a register-only reduction after tcgen05.ld.
+//            bias + ReLU commute with max and are applied once per (channel, centre).
+//
+// Persistent CTAs (grid = #SMs x resident CTAs), folded weights fetched once per CTA with TMA bulk
+// copies (cp.async.bulk + mbarrier), accumulators in TMEM (D3 aliases D2).
+#include "tc.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int SA_THREADS = 128;
+
+struct SaArgs {
+  const float* xyz;      // (B, N, 3)
+  const float* new_xyz;  // (B, npoint, 3)
+  const int* idx;        // (B, npoint, ns)
+  const float* g;        // (B*N, C1) fp32 or nullptr
+  const float* feat;     // (B, CD, N) fp32 or nullptr
+  const float* w1;       // (C1, 3 + CD) fp32, BatchNorm folded
+  const float* b1;       // (C1)
+  const uint8_t* w2p;    // packed (C2, C1)
+  const float* b2;
+  const uint8_t* w3p;    // packed (C3, C2)
+  const float* b3;
+  float* out_cm;         // (B, C3, npoint) fp32
+  __nv_bfloat16* out_pm; // (B*npoint, C3) bf16 or nullptr
+  int* err;
+  int B, N, npoint, ns, C1, C2, C3;
+  float radius_div;      // divisor applied to the recentred xyz (radius, or 1 when not normalised)
+  long long total_rows;  // B * npoint * ns
+};
+
+template <int CPL, int CD>  // channels per lane in layer 1 (C1 = 32 * CPL), raw feature channels
+__global__ void __launch_bounds__(SA_THREADS) sa_fused_kernel(const SaArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_w, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_b2[128], s_b3[256];
+
+  constexpr int C1 = 32 * CPL;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C2 = a.C2, C3 = a.C3, ns = a.ns;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w2_bytes = static_cast<uint32_t>(C2) * C1 * 2, w3_bytes = static_cast<uint32_t>(C3) * C2 * 2;
+  const uint32_t s_w2 = base, s_w3 = base + w2_bytes, s_x = base + w2_bytes + w3_bytes;  // all 1 KB multiples
+  const uint32_t tmem_cols = (C3 > 128 || C2 > 128) ? 256u : 128u;
+
+  if (tid == 0) {
+    mbar_init(&bar_w, 1);
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init_cluster();
+  }
+  for (int i = tid; i < C2; i += SA_THREADS) s_b2[i] = a.b2[i];
+  for (int i = tid; i < C3; i += SA_THREADS) s_b3[i] = a.b3[i];
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_d = tmem_slot;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_w, w2_bytes + w3_bytes);
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    tc::bulk_g2s(gen, a.w2p, w2_bytes, &bar_w);
+    tc::bulk_g2s(gen + w2_bytes, a.w3p, w3_bytes, &bar_w);
+  }
+
+  // layer-1 weights of this lane's channels, in registers for the whole kernel
+  float wx[CPL], wy[CPL], wz[CPL], wb[CPL], wf[CPL][CD > 0 ? CD : 1];
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    const int c = lane * CPL + q;
+    const float* row = a.w1 + static_cast<size_t>(c) * (3 + CD);
+    wx[q] = row[0]; wy[q] = row[1]; wz[q] = row[2]; wb[q] = a.b1[c];
+#pragma unroll
+    for (int d = 0; d < CD; ++d) wf[q][d] = row[3 + d];
+  }
+
+  const uint32_t idesc2 = tc::idesc_bf16_f32(128, C2);
+  const uint32_t idesc3 = tc::idesc_bf16_f32(128, 128);
+  const long long n_tiles = (a.total_rows + 127) / 128;
+  uint32_t phase = 0;
+  bool weights_ready = false, failed = false;
+
+  for (long long tile = blockIdx.x; tile < n_tiles && !failed; tile += gridDim.x) {
+    const long long r0 = tile * 128;
+    // ---------------- layer 1: build X1 (bf16) for rows warp*32 .. warp*32+31 -------------------
+    {
+      const long long R = r0 + warp * 32 + lane;  // the row this lane prepares geometry for
+      const bool ok = R < a.total_rows;
+      float rx = 0.f, ry = 0.f, rz = 0.f, fd[CD > 0 ? CD : 1];
+      long long grow = 0;  // row of g / point id within the batch-flattened cloud
+#pragma unroll
+      for (int d = 0; d < (CD > 0 ? CD : 1); ++d) fd[d] = 0.f;
+      if (ok) {
+        const long long jg = R / ns;  // global centre index b*npoint + j
+        const int b = static_cast<int>(jg / a.npoint);
+        const int pi = __ldg(a.idx + R);
+        grow = static_cast<long long>(b) * a.N + pi;
+        const float* p = a.xyz + grow * 3;
+        const float* c = a.new_xyz + jg * 3;
+        // pointnet2_utils.py:345-348: grouped_xyz -= new_xyz; grouped_xyz /= radius  (fp32 divide)
+        rx = __fdiv_rn(__ldg(p) - __ldg(c), a.radius_div);
+        ry = __fdiv_rn(__ldg(p + 1) - __ldg(c + 1), a.radius_div);
+        rz = __fdiv_rn(__ldg(p + 2) - __ldg(c + 2), a.radius_div);
+#pragma unroll
+        for (int d = 0; d < CD; ++d) fd[d] = __ldg(a.feat + (static_cast<size_t>(b) * CD + d) * a.N + pi);
+      }
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const float x = __shfl_sync(0xffffffffu, rx, i), y = __shfl_sync(0xffffffffu, ry, i),
+                    z = __shfl_sync(0xffffffffu, rz, i);
+        const bool rok = __shfl_sync(0xffffffffu, static_cast<int>(ok), i) != 0;
+        float v[CPL];
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) v[q] = __fmaf_rn(wz[q], z, __fmaf_rn(wy[q], y, __fmaf_rn(wx[q], x, wb[q])));
+        if (CD > 0) {
+#pragma unroll
+          for (int d = 0; d < CD; ++d) {
+            const float f = __shfl_sync(0xffffffffu, fd[d], i);
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) v[q] = __fmaf_rn(wf[q][d], f, v[q]);
+          }
+        }
+        if (a.g != nullptr) {
+          const long long gr = __shfl_sync(0xffffffffu, grow, i);
+          if (rok) {
+            if (CPL == 4) {
+              const float4 gv = __ldg(reinterpret_cast<const float4*>(a.g + gr * C1) + lane);
+              v[0] += gv.x; v[1] += gv.y; v[2] += gv.z; v[3] += gv.w;
+            } else {
+              const float2 gv = __ldg(reinterpret_cast<const float2*>(a.g + gr * C1) + lane);
+              v[0] += gv.x; v[1] += gv.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) v[q] = rok ? fmaxf(v[q], 0.f) : 0.f;
+        const uint32_t row = warp * 32 + i;
+        const uint32_t c0 = lane * CPL;              // first channel of this lane
+        const uint32_t chunk = c0 >> 3;               // 16-byte chunk along K
+        const uint32_t addr = s_x + (chunk >> 3) * (128u * 128u) + tc::swz_off(row, chunk & 7u) + (c0 & 7u) * 2u;
+        if (CPL == 4) {
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(tc::pack_bf16(v[0], v[1])),
+                       "r"(tc::pack_bf16(v[2], v[3]))
+                       : "memory");
+        } else {
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(tc::pack_bf16(v[0], v[1])) : "memory");
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (!weights_ready) {
+      if (!mbar_wait(&bar_w, 0)) { failed = true; break; }
+      weights_ready = true;
+    }
+    // ---------------- layer 2: D2 = X1 . W2^T --------------------------------------------------
+    if (tid == 0) {
+      tc::fence_after_sync();
+#pragma unroll
+      for (int kk = 0; kk < C1 / 16; ++kk) {
+        const uint32_t po = (kk >> 2), ko = (kk & 3) * 32;
+        tc::mma_bf16(tmem_d, tc::smem_desc_sw128(s_x + po * (128u * 128u) + ko),
+                     tc::smem_desc_sw128(s_w2 + po * (static_cast<uint32_t>(C2) * 128u) + ko), idesc2, kk > 0 ? 1u : 0u);
+      }
+      tc::mma_commit(&bar_mma);
+    }
+    if (!mbar_wait(&bar_mma, phase)) { failed = true; break; }
+    phase ^= 1;
+    tc::fence_after_sync();
+    // ---------------- epilogue 2: thread = row; bias + ReLU -> bf16 X2 over X1 ----------------
+    {
+      const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+      for (int c0 = 0; c0 < C2; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(lane_base + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + s_b2[c0 + i], 0.f);
+        const uint32_t chunk = c0 >> 3;
+        const uint32_t pa = s_x + (chunk >> 3) * (128u * 128u);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa + tc::swz_off(tid, chunk & 7u)),
+                     "r"(tc::pack_bf16(v[0], v[1])), "r"(tc::pack_bf16(v[2], v[3])), "r"(tc::pack_bf16(v[4], v[5])),
+                     "r"(tc::pack_bf16(v[6], v[7]))
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa + tc::swz_off(tid, (chunk + 1) & 7u)),
+                     "r"(tc::pack_bf16(v[8], v[9])), "r"(tc::pack_bf16(v[10], v[11])),
+                     "r"(tc::pack_bf16(v[12], v[13])), "r"(tc::pack_bf16(v[14], v[15]))
+                     : "memory");
+      }
+    }
+    fence_proxy_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    // ---------------- layer 3 (transposed): D3[h] = W3[h*128 .. +128] . X2^T -------------------
+    if (tid == 0) {
+      tc::fence_after_sync();
+      for (int h = 0; h < C3 / 128; ++h) {
+        for (int kk = 0; kk < C2 / 16; ++kk) {
+          const uint32_t po = (kk >> 2), ko = (kk & 3) * 32;
+          tc::mma_bf16(tmem_d + h * 128,
+                       tc::smem_desc_sw128(s_w3 + po * (static_cast<uint32_t>(C3) * 128u) + h * (128u * 128u) + ko),
+                       tc::smem_desc_sw128(s_x + po * (128u * 128u) + ko), idesc3, kk > 0 ? 1u : 0u);
+        }
+      }
+      tc::mma_commit(&bar_mma);
+    }
+    if (!mbar_wait(&bar_mma, phase)) { failed = true; break; }
+    phase ^= 1;
+    tc::fence_after_sync();
+    // ---------------- epilogue 3: thread = channel; max over each centre's ns columns ----------
+    {
+      const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+      const int groups = 128 / ns;
+      for (int h = 0; h < C3 / 128; ++h) {
+        const int ch = h * 128 + tid;
+        const float bias = s_b3[ch];
+        for (int gidx = 0; gidx < groups; ++gidx) {
+          float mx = -INFINITY;
+          for (int c0 = 0; c0 < ns; c0 += 16) {
+            float v[16];
+            tc::tmem_ld16(lane_base + h * 128 + gidx * ns + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+          }
+          const long long jg = r0 / ns + gidx;  // global centre index
+          if (jg * ns < a.total_rows) {
+            const float o = fmaxf(mx + bias, 0.f);
+            const long long b = jg / a.npoint, j = jg - b * a.npoint;
+            a.out_cm[(b * C3 + ch) * a.npoint + j] = o;
+            if (a.out_pm) a.out_pm[jg * C3 + ch] = __float2bfloat16_rn(o);
+          }
+        }
+      }
+    }
+    tc::fence_before_sync();  // ordered before the next tile's __syncthreads / MMA into the same TMEM
+  }
+  if (failed && tid == 0) atomicExch(a.err, 2);
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
+}
+
+template <int CPL>
+int launch_cd(int cd, const SaArgs& a, int grid, size_t smem, cudaStream_t s) {
+#define PN2_SA_CASE(CDV)                                                                                   \
+  case CDV: {                                                                                              \
+    PN2_CUDA(cudaFuncSetAttribute(sa_fused_kernel<CPL, CDV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  static_cast<int>(smem)));                                                \
+    sa_fused_kernel<CPL, CDV><<<grid, SA_THREADS, smem, s>>>(a);                                           \
+    break;                                                                                                 \
+  }
+  switch (cd) {
+    PN2_SA_CASE(0) PN2_SA_CASE(1) PN2_SA_CASE(2) PN2_SA_CASE(3) PN2_SA_CASE(4)
+    default: set_error("sa_group_mlp: direct feature channels must be <= 4 (got %d)", cd); return PN2_ERR_INVALID;
+  }
+#undef PN2_SA_CASE
+  PN2_CHECK_LAUNCH("sa_fused_kernel");
+  return PN2_OK;
+}
+
+}  // namespace
+
+int* device_err_flag();
+
+}  // namespace pn2
+
+using namespace pn2;
+
+extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float radius_div, const float* xyz,
+                                const float* new_xyz, const int* idx, int c_direct, const float* feat,
+                                const float* g, int c1, int c2, int c3, const float* w1, const float* b1,
+                                const void* w2_packed, const float* b2, const void* w3_packed, const float* b3,
+                                float* out_cm, void* out_pm_bf16, void* stream) {
+  if (b <= 0 || npoint <= 0) return PN2_OK;
+  PN2_REQUIRE(nsample == 16 || nsample == 32 || nsample == 64 || nsample == 128,
+              "sa_group_mlp: nsample=%d must be 16, 32, 64 or 128", nsample);
+  PN2_REQUIRE((c1 == 64 || c1 == 128) && (c2 == 64 || c2 == 128) && (c3 == 128 || c3 == 256),
+              "sa_group_mlp: unsupported widths %d/%d/%d (c1,c2 in {64,128}, c3 in {128,256})", c1, c2, c3);
+  PN2_REQUIRE(xyz && new_xyz && idx && w1 && b1 && w2_packed && b2 && w3_packed && b3 && out_cm && n > 0,
+              "sa_group_mlp: null pointer");
+  PN2_REQUIRE(c_direct >= 0 && c_direct <= 4 && (c_direct == 0 || feat), "sa_group_mlp: bad direct features");
+  PN2_REQUIRE(radius_div != 0.f, "sa_group_mlp: radius_div must be non-zero");
+  SaArgs a;
+  a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx; a.g = g; a.feat = feat; a.w1 = w1; a.b1 = b1;
+  a.w2p = static_cast<const uint8_t*>(w2_packed); a.b2 = b2; a.w3p = static_cast<const uint8_t*>(w3_packed); a.b3 = b3;
+  a.out_cm = out_cm; a.out_pm = static_cast<__nv_bfloat16*>(out_pm_bf16);
+  a.B = b; a.N = n; a.npoint = npoint; a.ns = nsample; a.C1 = c1; a.C2 = c2; a.C3 = c3;
+  a.radius_div = radius_div;
+  a.total_rows = static_cast<long long>(b) * npoint * nsample;
+  a.err = device_err_flag();
+  PN2_REQUIRE(a.err != nullptr, "sa_group_mlp: cannot allocate the device error flag");
+  const size_t smem = static_cast<size_t>(c2) * c1 * 2 + static_cast<size_t>(c3) * c2 * 2 +
+                      128 * static_cast<size_t>(c1 > c2 ? c1 : c2) * 2 + 1024;
+  const long long tiles = (a.total_rows + 127) / 128;
+  const int per_sm = smem <= 56 * 1024 ? 4 : (smem <= 113 * 1024 ? 2 : 1);
+  const int tm_cols = (c3 > 128 || c2 > 128) ? 256 : 128;
+  const int per_sm_tm = 512 / tm_cols;
+  const int resident = per_sm < per_sm_tm ? per_sm : per_sm_tm;
+  long long grid = static_cast<long long>(sm_count()) * resident;
+  if (grid > tiles) grid = tiles;
+  cudaStream_t s = as_stream(stream);
+  if (c1 == 128) return launch_cd<4>(c_direct, a, static_cast<int>(grid), smem, s);
+  return launch_cd<2>(c_direct, a, static_cast<int>(grid), smem, s);
+}

@@ -1,11 +1,135 @@
-"""Fused eval-mode paths for the SA / FP modules (filled in as the tcgen05 kernels land).
+"""Fused eval-mode execution of the SA / FP modules on the sm_100a kernels.
 
-Returning None tells the module to use its generic op-by-op path.
+``sa_forward`` replaces the body of PointnetSAModuleVotes.forward (reference
+pointnet2_modules.py:233-270) by four launches -- FPS+gather, ball query, (for wide inputs) one
+tensor-core GEMM over the input points, and the fused grouping + shared-MLP + max-pool kernel --
+with BatchNorm folded into the convolution weights (eval mode: running statistics, eps as in the
+module).  Returning None tells the caller to use its generic op-by-op path (training, odd shapes).
+
+Numerics of the fused path (the contract the tests assert, tests/test_fused_gpu.py):
+every tensor-core operand (activations, folded weights) is rounded to bf16 (RNE); products are
+exact and accumulate in fp32; the geometric half of layer 1 (3 FMAs per channel on the recentred,
+radius-divided coordinates) and up to 4 raw feature channels are evaluated in fp32.
 """
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _ext
+from . import _lib as L
+from . import tensorcore as tcm
+
+_NS_OK = (16, 32, 64, 128)
+
+
+def _fold_block(block):
+    """Conv (1x1, optional bias) + optional BatchNorm(eval) -> (W' (out,in), b' (out)) in fp32."""
+    conv = block.conv
+    w = conv.weight.detach().float().reshape(conv.weight.shape[0], -1)
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    if hasattr(block, "bn"):
+        bn = block.bn.bn
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * scale[:, None]
+        b = (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    return w.contiguous(), b.contiguous()
+
+
+def _plain_relu_mlp(mlp, n_layers):
+    """True if `mlp` is a SharedMLP of exactly n_layers post-activation conv(+bn)+ReLU blocks."""
+    blocks = list(mlp.children())
+    if len(blocks) != n_layers:
+        return False
+    for blk in blocks:
+        names = [n for n, _ in blk.named_children()]
+        if names not in (["conv", "bn", "activation"], ["conv", "activation"]):
+            return False
+        if not isinstance(blk.activation, nn.ReLU):
+            return False
+        if tuple(blk.conv.kernel_size) != (1,) * len(blk.conv.kernel_size):
+            return False
+    return True
+
+
+def _version_key(module):
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+class _SaPlan:
+    def __init__(self, module):
+        blocks = list(module.mlp_module.children())
+        w1, self.b1 = _fold_block(blocks[0])
+        w2, self.b2 = _fold_block(blocks[1])
+        w3, self.b3 = _fold_block(blocks[2])
+        self.c1, self.c2, self.c3 = w1.shape[0], w2.shape[0], w3.shape[0]
+        self.c_in = w1.shape[1] - 3
+        self.direct = self.c_in <= 4
+        if self.direct:
+            self.w1 = w1.contiguous()
+            self.w1f = None
+        else:
+            self.w1 = w1[:, :3].contiguous()
+            self.w1f = tcm.PackedWeight(w1[:, 3:].contiguous())
+        self.w2p = tcm.PackedWeight(w2)
+        self.w3p = tcm.PackedWeight(w3)
+        self.key = _version_key(module)
+
+    @staticmethod
+    def supported(module):
+        if not (module.use_xyz and module.pooling == "max" and module.nsample in _NS_OK):
+            return False
+        if not _plain_relu_mlp(module.mlp_module, 3):
+            return False
+        blocks = list(module.mlp_module.children())
+        c1, c2, c3 = (b.conv.out_channels for b in blocks)
+        if blocks[0].conv.in_channels < 3:
+            return False
+        return c1 in (64, 128) and c2 in (64, 128) and c3 in (128, 256)
 
 
 def sa_forward(module, xyz, features, inds):
-    return None
+    if module._fused is False:
+        return None
+    if module._fused is None or module._fused.key != _version_key(module):
+        if not _SaPlan.supported(module):
+            module._fused = False
+            return None
+        module._fused = _SaPlan(module)
+    plan = module._fused
+    c_feat = 0 if features is None else features.shape[1]
+    if c_feat != plan.c_in or xyz.dtype != torch.float32:
+        return None
+    xyz = xyz.contiguous()
+    b, n = xyz.shape[0], xyz.shape[1]
+    dev = xyz.device
+
+    if inds is None:
+        inds, new_xyz = _ext.furthest_point_sampling_gather(xyz, module.npoint)
+    else:
+        new_xyz = torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    idx = _ext.ball_query(new_xyz, xyz, module.radius, module.nsample)
+
+    g = None
+    feat = None
+    if plan.direct:
+        if c_feat:
+            feat = features.contiguous().float()
+    else:
+        rows = getattr(features, "_pn2_rows", None)
+        if rows is None or rows.shape != (b * n, plan.w1f.kpad) or rows.device != dev:
+            rows = tcm.pack_rows(features.contiguous().float(), plan.w1f.kpad)
+        g = tcm.linear(rows, plan.w1f, None, relu=False, out="f32")
+
+    out_cm = torch.empty(b, plan.c3, module.npoint, device=dev, dtype=torch.float32)
+    out_pm = torch.empty(b * module.npoint, plan.c3, device=dev, dtype=torch.bfloat16)
+    radius_div = float(module.radius) if module.normalize_xyz else 1.0
+    L.call("pn2_sa_group_mlp", b, n, module.npoint, module.nsample, ctypes.c_float(radius_div), L.ptr(xyz),
+           L.ptr(new_xyz), L.ptr(idx), plan.c_in if plan.direct else 0, L.ptr(feat), L.ptr(g), plan.c1, plan.c2,
+           plan.c3, L.ptr(plan.w1), L.ptr(plan.b1), L.ptr(plan.w2p.data), L.ptr(plan.b2), L.ptr(plan.w3p.data),
+           L.ptr(plan.b3), L.ptr(out_cm), L.ptr(out_pm), L.stream_of(xyz), device=dev)
+    out_cm._pn2_rows = out_pm  # bf16 point-major twin: the next SA layer's GEMM operand, no repack
+    return new_xyz, out_cm, inds
 
 
 def fp_forward(module, unknown, known, unknow_feats, known_feats):

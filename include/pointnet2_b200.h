@@ -144,6 +144,24 @@ int pn2_pack_rows_bf16(int b, int c, int n, int kpad, const float* features, voi
 int pn2_linear_bf16(int m, int n, int k, const void* x_bf16, const void* w_packed, const float* bias,
                     int relu, int out_mode, int rows_per_batch, void* y, void* stream);
 
+/* Fused body of a set-abstraction layer (pointnet2_modules.py:243-257: QueryAndGroup -> SharedMLP
+ * (3 layers) -> max_pool2d over nsample), eval mode, BatchNorm folded.  Grouping, the three 1x1
+ * convolutions and the max-pool run in one kernel; only the pooled result is written.
+ *   xyz (b,n,3), new_xyz (b,npoint,3), idx (b,npoint,nsample) from pn2_ball_query;
+ *   radius_div: divisor of the recentred coordinates (radius when normalize_xyz, else 1);
+ *   layer 1 = w1 (c1, 3 + c_direct) fp32 . [rel_xyz, feat] + b1 (+ g): `feat` (b,c_direct,n) are up
+ *   to 4 raw channels evaluated in fp32; `g` (b*n, c1) fp32, if non-NULL, is the per-point
+ *   contribution W1[:,3:] . features precomputed with pn2_linear_bf16 (wide inputs);
+ *   w2_packed (c2,c1), w3_packed (c3,c2) from pn2_pack_weight_bf16; b1/b2/b3 fp32 folded biases;
+ *   c1,c2 in {64,128}, c3 in {128,256}, nsample in {16,32,64,128}.
+ * Outputs: out_cm (b,c3,npoint) fp32 -- the reference's feature layout -- and, if non-NULL,
+ * out_pm_bf16 (b*npoint, c3) bf16 point-major rows ready to be the next layer's GEMM operand. */
+int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float radius_div, const float* xyz,
+                     const float* new_xyz, const int* idx, int c_direct, const float* feat,
+                     const float* g, int c1, int c2, int c3, const float* w1, const float* b1,
+                     const void* w2_packed, const float* b2, const void* w3_packed, const float* b3,
+                     float* out_cm, void* out_pm_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -282,6 +282,56 @@ def fp_module(unknown, known, unknow_feats, known_feats, sd, prefix, n_layers=2,
     return x.squeeze(-1)
 
 
+def _bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def fold_bn(sd, prefix, i, eps=1e-5):
+    """Conv + eval-mode BatchNorm of layer i folded into (W' (out,in), b' (out)), fp32."""
+    w = sd[f"{prefix}layer{i}.conv.weight"].float()
+    w = w.reshape(w.shape[0], -1)
+    b = sd.get(f"{prefix}layer{i}.conv.bias")
+    b = b.float() if b is not None else torch.zeros(w.shape[0])
+    p = f"{prefix}layer{i}.bn.bn."
+    if p + "weight" in sd:
+        scale = sd[p + "weight"].float() / torch.sqrt(sd[p + "running_var"].float() + eps)
+        w = w * scale[:, None]
+        b = (b - sd[p + "running_mean"].float()) * scale + sd[p + "bias"].float()
+    return w, b
+
+
+def sa_module_mixed(xyz, features, sd, prefix, npoint, radius, nsample, normalize_xyz=True, inds=None):
+    """The fused SA path's numerics contract restated in torch (eval mode, 3-layer MLP, max pool):
+    bf16-rounded operands for every tensor-core contraction, exact products, fp32 accumulation;
+    geometric half of layer 1 and <= 4 raw feature channels in fp32.  See 3dvlp_b200/fused.py."""
+    xyz = xyz.contiguous()
+    if inds is None:
+        inds = ext.furthest_point_sampling(xyz, npoint)
+    new_xyz = ext.gather_points(xyz.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
+    idx = ext.ball_query(new_xyz, xyz, radius, nsample)
+    gx = ext.group_points(xyz.transpose(1, 2).contiguous(), idx) - new_xyz.transpose(1, 2).unsqueeze(-1)
+    if normalize_xyz:
+        gx = gx / radius
+    w1, b1 = fold_bn(sd, prefix + "mlp_module.", 0)
+    w2, b2 = fold_bn(sd, prefix + "mlp_module.", 1)
+    w3, b3 = fold_bn(sd, prefix + "mlp_module.", 2)
+    y = torch.einsum("oc,bcms->boms", w1[:, :3].double(), gx.double()) + b1.double()[None, :, None, None]
+    c_in = w1.shape[1] - 3
+    if c_in:
+        if c_in <= 4:
+            gf = ext.group_points(features.contiguous(), idx)
+            y = y + torch.einsum("oc,bcms->boms", w1[:, 3:].double(), gf.double())
+        else:
+            g = torch.einsum("oc,bcn->bon", _bf16r(w1[:, 3:]).double(), _bf16r(features).double()).float()
+            y = y + ext.group_points(g.contiguous(), idx).double()
+    x1 = _bf16r(torch.relu(y).float())
+    y2 = torch.einsum("oc,bcms->boms", _bf16r(w2).double(), x1.double()) + b2.double()[None, :, None, None]
+    x2 = _bf16r(torch.relu(y2).float())
+    y3 = torch.einsum("oc,bcms->boms", _bf16r(w3).double(), x2.double())
+    out = torch.relu(y3.max(dim=3).values + b3.double()[None, :, None]).float()
+    return new_xyz, out, inds
+
+
 BACKBONE_SA = (  # backbone_module.py:29-63: (name, npoint, radius, nsample)
     ("sa1", 2048, 0.2, 64), ("sa2", 1024, 0.4, 32), ("sa3", 512, 0.8, 16), ("sa4", 256, 1.2, 16))
 
