@@ -1,0 +1,118 @@
+// Feature-propagation front end: three_nn + inverse-distance weights + three_interpolate + skip
+// concatenation, fused into ONE kernel that writes the bf16 point-major operand of the FP shared MLP.
+//
+// Reference path (pointnet2_modules.py:393-412): three_nn kernel -> sqrt -> 1/(d+1e-8) -> sum -> div
+// (4 torch kernels) -> three_interpolate kernel -> torch.cat -> unsqueeze -> cuDNN 1x1 convs.  Here a
+// CTA owns 32 unknown points: warp 0 finds the three nearest known points (known xyz staged in
+// shared memory, the strict-`<` cascade of interpolate_gpu.cu:39-55 so ties keep the earlier index)
+// and the weights; then all warps interpolate 64 channels at a time (lane = point, so the skip
+// features are read coalesced from the reference's (B, C, n) layout), transpose through shared
+// memory and store 128-byte row segments of  X[b*n + j][0 : C2 + C1]  in bf16 -- the K-major
+// activation matrix that pn2_linear_bf16 (tcgen05) consumes.  Interpolated channels come first,
+// skip channels second (torch.cat([interpolated, unknow_feats], dim=1)).
+#include "tc.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int FP_THREADS = 128;
+constexpr int FP_KTILE = 1024;  // known points staged per pass (12 KB)
+
+__global__ void __launch_bounds__(FP_THREADS)
+fp_prepare_kernel(int n, int m, int c1, int c2, int kpad, const float* __restrict__ unknown,
+                  const float* __restrict__ known, const float* __restrict__ uf, const float* __restrict__ kf,
+                  __nv_bfloat16* __restrict__ out) {
+  __shared__ float sk[FP_KTILE * 3];
+  __shared__ int s_idx[32][3];
+  __shared__ float s_w[32][3];
+  __shared__ float tile[32][65];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int scene = blockIdx.y, p0 = blockIdx.x * 32;
+  unknown += static_cast<size_t>(scene) * n * 3;
+  known += static_cast<size_t>(scene) * m * 3;
+  const float* kfb = kf + static_cast<size_t>(scene) * c2 * m;
+  const float* ufb = uf ? uf + static_cast<size_t>(scene) * c1 * n : nullptr;
+
+  // ---- three nearest known points + weights for the CTA's 32 unknown points --------------------
+  const int j = p0 + lane;
+  float ux = 0.f, uy = 0.f, uz = 0.f;
+  if (warp == 0 && j < n) { ux = __ldg(unknown + 3 * j); uy = __ldg(unknown + 3 * j + 1); uz = __ldg(unknown + 3 * j + 2); }
+  float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int t0 = 0; t0 < m; t0 += FP_KTILE) {
+    const int tn = min(FP_KTILE, m - t0);
+    __syncthreads();
+    for (int q = tid; q < tn * 3; q += FP_THREADS) sk[q] = __ldg(known + 3 * t0 + q);
+    __syncthreads();
+    if (warp == 0 && j < n) {
+      for (int k = 0; k < tn; ++k) {
+        const float d = sqdist3(ux - sk[3 * k], uy - sk[3 * k + 1], uz - sk[3 * k + 2]);
+        if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = t0 + k; }
+        else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = t0 + k; }
+        else if (d < b3) { b3 = d; i3 = t0 + k; }
+      }
+    }
+  }
+  if (warp == 0) {
+    // pointnet2_utils.py:138-140 (sqrt) and pointnet2_modules.py:395-397 (1/(d+1e-8), normalise)
+    const float r1 = __fdiv_rn(1.0f, __fsqrt_rn(b1) + 1e-8f), r2 = __fdiv_rn(1.0f, __fsqrt_rn(b2) + 1e-8f),
+                r3 = __fdiv_rn(1.0f, __fsqrt_rn(b3) + 1e-8f);
+    const float norm = (r1 + r2) + r3;
+    s_idx[lane][0] = i1; s_idx[lane][1] = i2; s_idx[lane][2] = i3;
+    s_w[lane][0] = __fdiv_rn(r1, norm); s_w[lane][1] = __fdiv_rn(r2, norm); s_w[lane][2] = __fdiv_rn(r3, norm);
+  }
+  __syncthreads();
+  const int a1 = s_idx[lane][0], a2 = s_idx[lane][1], a3 = s_idx[lane][2];
+  const float w1 = s_w[lane][0], w2 = s_w[lane][1], w3 = s_w[lane][2];
+  const bool live = j < n;
+
+  // ---- 64 channels per pass: lane = point, warp = 16-channel slice; transpose; store ----------
+  for (int ch0 = 0; ch0 < kpad; ch0 += 64) {
+#pragma unroll 4
+    for (int cc = 0; cc < 16; ++cc) {
+      const int c = ch0 + warp * 16 + cc;
+      float v = 0.f;
+      if (live) {
+        if (c < c2) {
+          const float* p = kfb + static_cast<size_t>(c) * m;
+          v = __fmaf_rn(__ldg(p + a3), w3, __fmaf_rn(__ldg(p + a1), w1, __fmul_rn(__ldg(p + a2), w2)));
+        } else if (c < c2 + c1) {
+          v = __ldg(ufb + static_cast<size_t>(c - c2) * n + j);
+        }
+      }
+      tile[lane][warp * 16 + cc] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int q = tid + FP_THREADS * i;
+      const int pt = q >> 3, piece = q & 7;
+      if (p0 + pt < n) {
+        const float* t = &tile[pt][piece * 8];
+        const uint4 pk = make_uint4(tc::pack_bf16(t[0], t[1]), tc::pack_bf16(t[2], t[3]), tc::pack_bf16(t[4], t[5]),
+                                    tc::pack_bf16(t[6], t[7]));
+        *reinterpret_cast<uint4*>(out + (static_cast<size_t>(scene) * n + p0 + pt) * kpad + ch0 + piece * 8) = pk;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+}  // namespace pn2
+
+using namespace pn2;
+
+extern "C" int pn2_fp_prepare(int b, int n, int m, int c1, int c2, int kpad, const float* unknown,
+                              const float* known, const float* unknow_feats, const float* known_feats,
+                              void* out_bf16, void* stream) {
+  if (b <= 0 || n <= 0) return PN2_OK;
+  PN2_REQUIRE(m > 0 && c2 > 0 && c1 >= 0 && kpad >= c1 + c2 && kpad % 64 == 0, "fp_prepare: bad sizes");
+  PN2_REQUIRE(unknown && known && known_feats && out_bf16 && (c1 == 0 || unknow_feats) && b <= 65535,
+              "fp_prepare: bad arguments");
+  dim3 grid((n + 31) / 32, b);
+  fp_prepare_kernel<<<grid, FP_THREADS, 0, as_stream(stream)>>>(n, m, c1, c2, kpad, unknown, known, unknow_feats,
+                                                               known_feats, static_cast<__nv_bfloat16*>(out_bf16));
+  PN2_CHECK_LAUNCH("fp_prepare_kernel");
+  return PN2_OK;
+}

@@ -132,5 +132,54 @@ def sa_forward(module, xyz, features, inds):
     return new_xyz, out_cm, inds
 
 
+class _FpPlan:
+    def __init__(self, module):
+        self.layers = []
+        for blk in module.mlp.children():
+            w, b = _fold_block(blk)
+            self.layers.append((tcm.PackedWeight(w), b))
+        self.c_in = self.layers[0][0].k
+        self.key = _version_key(module)
+
+    @staticmethod
+    def supported(module):
+        blocks = list(module.mlp.children())
+        if not blocks or not _plain_relu_mlp(module.mlp, len(blocks)):
+            return False
+        outs = [b.conv.out_channels for b in blocks]
+        if any(o % 16 or o > 256 for o in outs):
+            return False
+        return all(o % 64 == 0 for o in outs[:-1])  # a hidden width is the next layer's K
+
+
 def fp_forward(module, unknown, known, unknow_feats, known_feats):
-    return None
+    """PointnetFPModule.forward (pointnet2_modules.py:371-416) in 1 + n_layers launches: the fused
+    three_nn/interpolate/concat front end, then one tcgen05 linear kernel per MLP layer (the last
+    one stores straight into the reference's (B, C, n) layout)."""
+    if module._fused is False:
+        return None
+    if module._fused is None or module._fused.key != _version_key(module):
+        if not _FpPlan.supported(module):
+            module._fused = False
+            return None
+        module._fused = _FpPlan(module)
+    plan = module._fused
+    b, n = unknown.shape[0], unknown.shape[1]
+    m = known.shape[1]
+    c1 = unknow_feats.shape[1] if unknow_feats is not None else 0
+    c2 = known_feats.shape[1]
+    if c1 + c2 != plan.c_in or known_feats.shape[2] != m or unknown.dtype != torch.float32:
+        return None
+    dev = unknown.device
+    kpad = plan.layers[0][0].kpad
+    x = torch.empty(b * n, kpad, device=dev, dtype=torch.bfloat16)
+    uf = unknow_feats.contiguous().float() if unknow_feats is not None else None
+    L.call("pn2_fp_prepare", b, n, m, c1, c2, kpad, L.ptr(unknown.contiguous()), L.ptr(known.contiguous()),
+           L.ptr(uf), L.ptr(known_feats.contiguous().float()), L.ptr(x), L.stream_of(unknown), device=dev)
+    last = len(plan.layers) - 1
+    for i, (w, bias) in enumerate(plan.layers):
+        if i < last:
+            x = tcm.linear(x, w, bias, relu=True, out="bf16")
+        else:
+            x = tcm.linear(x, w, bias, relu=True, out="cm", rows_per_batch=n)
+    return x

@@ -162,6 +162,15 @@ int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float radius_div, co
                      const void* w2_packed, const float* b2, const void* w3_packed, const float* b3,
                      float* out_cm, void* out_pm_bf16, void* stream);
 
+/* Front end of a feature-propagation layer (pointnet2_modules.py:393-412: three_nn -> sqrt ->
+ * 1/(d+1e-8) normalised weights -> three_interpolate -> cat([interpolated, unknow_feats])), fused:
+ * unknown (b,n,3), known (b,m,3), unknow_feats (b,c1,n) or NULL (c1 = 0), known_feats (b,c2,m), all
+ * fp32 in the reference's layouts -> out_bf16 (b*n, kpad) bf16 rows [interp c2 | skip c1 | zero pad],
+ * kpad % 64 == 0: the activation operand of pn2_linear_bf16. */
+int pn2_fp_prepare(int b, int n, int m, int c1, int c2, int kpad, const float* unknown,
+                   const float* known, const float* unknow_feats, const float* known_feats,
+                   void* out_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -332,6 +332,21 @@ def sa_module_mixed(xyz, features, sd, prefix, npoint, radius, nsample, normaliz
     return new_xyz, out, inds
 
 
+def fp_module_mixed(unknown, known, unknow_feats, known_feats, sd, prefix, n_layers=2):
+    """Numerics contract of the fused FP path: fp32 3-NN / weights / interpolation, then every MLP
+    layer as a bf16 x bf16 -> fp32 contraction with folded BatchNorm (hidden activations bf16)."""
+    dist2, idx = ext.three_nn(unknown.contiguous(), known.contiguous())
+    r = 1.0 / (torch.sqrt(dist2) + 1e-8)
+    w = r / torch.sum(r, dim=2, keepdim=True)
+    interp = ext.three_interpolate(known_feats.contiguous(), idx, w.contiguous())
+    x = torch.cat([interp, unknow_feats], dim=1) if unknow_feats is not None else interp
+    for i in range(n_layers):
+        wgt, b = fold_bn(sd, prefix + "mlp.", i)
+        x = torch.relu(torch.einsum("oc,bcn->bon", _bf16r(wgt).double(), _bf16r(x).double())
+                       + b.double()[None, :, None]).float()
+    return x
+
+
 BACKBONE_SA = (  # backbone_module.py:29-63: (name, npoint, radius, nsample)
     ("sa1", 2048, 0.2, 64), ("sa2", 1024, 0.4, 32), ("sa3", 512, 0.8, 16), ("sa4", 256, 1.2, 16))
 

@@ -116,3 +116,49 @@ def test_sa_fused_user_inds_and_unnormalised(pkg, oracle, cuda):
     wx, wf, _ = oracle.sa_module_mixed(xyz, feats, sd, "", 64, 0.4, 16, normalize_xyz=False, inds=inds)
     assert torch.equal(nx.cpu(), wx) and torch.equal(ii.cpu(), inds)
     torch.testing.assert_close(nf.cpu(), wf, rtol=1e-3, atol=2e-3 * wf.abs().max().item())
+
+
+@pytest.mark.parametrize("n,m,c1,c2,mlp", [(512, 256, 256, 256, [256, 256]), (1024, 512, 256, 256, [256, 256]),
+                                          (300, 70, 19, 45, [128, 64]), (50, 2, 0, 12, [64])])
+def test_fp_fused_matches_mixed_precision_contract(pkg, oracle, cuda, n, m, c1, c2, mlp):
+    from common import cloud, fill_state_dict
+    unknown = cloud(31 + n, 2, n, extent=1.0)[..., :3].contiguous()
+    known = cloud(32 + m, 2, m, extent=1.0)[..., :3].contiguous()
+    if m > 3:
+        known[:, 3] = unknown[:, 7]
+    g = torch.Generator().manual_seed(n + m)
+    uf = torch.randn(2, c1, n, generator=g) if c1 else None
+    kf = torch.randn(2, c2, m, generator=g)
+    fp = pkg.PointnetFPModule(mlp=[c1 + c2] + mlp)
+    sd = fill_state_dict(fp)
+    fp = fp.to(cuda).eval()
+    with torch.no_grad():
+        got = fp(unknown.to(cuda), known.to(cuda), None if uf is None else uf.to(cuda), kf.to(cuda))
+    if c1 == 0:
+        assert fp._fused is None  # unknow_feats=None takes the generic path by design
+        return
+    assert fp._fused not in (None, False), "fused path was not taken"
+    want = oracle.fp_module_mixed(unknown, known, uf, kf, sd, "", n_layers=len(mlp))
+    scale = want.abs().max().item()
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-3, atol=4e-3 * scale)
+    ref = oracle.fp_module(unknown, known, uf, kf, sd, "", n_layers=len(mlp))
+    assert (got.cpu() - ref).abs().max().item() / ref.abs().max().item() < 2e-2
+
+
+def test_backbone_fused_vs_oracle(pkg, oracle, cuda):
+    """Whole backbone through the fused path on a 5000-point scene: indices/coordinates bit-exact,
+    features within the mixed-precision tolerance of the fp32 reference semantics."""
+    from common import cloud, fill_state_dict
+    bb = pkg.Pointnet2Backbone(input_feature_dim=1)
+    sd = fill_state_dict(bb)
+    bb = bb.to(cuda).eval()
+    scene = cloud(41, 2, 5000, c_extra=1, extent=1.6, dup_frac=0.05, origin_pts=4)
+    with torch.no_grad():
+        d = bb({"point_clouds": scene.to(cuda)})
+    want = oracle.backbone(scene, sd)
+    for k in ("sa1_inds", "sa2_inds", "fp2_inds", "sa1_xyz", "sa2_xyz", "sa3_xyz", "sa4_xyz", "fp2_xyz"):
+        assert torch.equal(d[k].cpu(), want[k]), k
+    for k in ("sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"):
+        err = (d[k].cpu() - want[k]).abs().max().item() / want[k].abs().max().item()
+        assert err < 3e-2, (k, err)
+    assert d["fp2_features"].shape == (2, 256, 1024) and d["fp2_inds"].dtype == torch.int32
