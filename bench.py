@@ -142,6 +142,59 @@ def cpu_reference_arm(args, torch, pkg, syn):
     print(json.dumps(line), flush=True)
 
 
+def reference_cuda_ext_leg(torch, pkg, model, dev_pool, steps):
+    """Time the UNMODIFIED reference CUDA extension (oracle/_ref/pointnet2_ref_ext.so, built by
+    oracle/build_ref.py) driving the same module tree op by op exactly like the reference's Python
+    layers (FPS -> gather -> ball_query -> group x2 -> cuDNN SharedMLP -> max_pool; three_nn ->
+    three_interpolate -> cuDNN MLP).  This is the "reference CUDA-extension semantics" bar of the
+    north star; it is a measured baseline, never part of the product path."""
+    import importlib.util
+    so = os.path.join(ROOT, "oracle", "_ref", "pointnet2_ref_ext.so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location("pointnet2_ref_ext", so)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+
+    class Shim:
+        def __getattr__(self, name):
+            return getattr(ref, name)
+
+        @staticmethod
+        def furthest_point_sampling_gather(xyz, npoint):  # pointnet2_modules.py:233-240
+            inds = ref.furthest_point_sampling(xyz, npoint)
+            flipped = xyz.transpose(1, 2).contiguous()
+            return inds, ref.gather_points(flipped, inds).transpose(1, 2).contiguous()
+
+    utils = pkg.pointnet2_utils
+    saved_ext = utils._ext
+    saved = {}
+    for name, m in model.named_modules():
+        if hasattr(m, "_fused"):
+            saved[name] = m._fused
+            m._fused = False  # generic op-by-op path
+    utils._ext = Shim()
+    try:
+        with torch.no_grad():
+            for s in range(2):
+                model({"point_clouds": dev_pool[s % POOL]})
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for s in range(steps):
+                model({"point_clouds": dev_pool[(2 + s) % POOL]})
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        utils._ext = saved_ext
+        for name, m in model.named_modules():
+            if name in saved:
+                m._fused = saved[name]
+    return {"value": SCENES_PER_GPU / (ms * 1e-3), "unit": "scenes/s", "ms_per_step": ms, "steps": steps,
+            "what": "unmodified reference _ext (sm_100a build) + torch/cuDNN layers, same inputs, 1 GPU"}
+
+
 def per_op_profile(torch, L, model, batch, reps=5):
     """Per-C-ABI-call device time with CUDA events on the launching stream (one forward per rep)."""
     acc = {}
@@ -291,6 +344,11 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_ops": roofline_ops[:24]}
+        if world == 1:
+            try:
+                line["ref_cuda_ext"] = reference_cuda_ext_leg(torch, pkg, model, dev_pool, min(args.steps, 5))
+            except Exception as ex:  # the baseline must never break the product's line
+                line["ref_cuda_ext"] = {"error": repr(ex)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             cores = os.cpu_count() or 1
