@@ -1,0 +1,235 @@
+// Ball query for large clouds through a hashed uniform grid -- same output as the linear scan,
+// two orders of magnitude fewer distance tests.
+//
+// Reference semantics (ball_query_gpu.cu:14-49): for every centre, the FIRST nsample point indices in
+// ascending order with d2 < r^2, padded with the first hit; an empty ball is a row of zeros.  The
+// reference (and csrc/search.cu for small clouds) scans all n points per centre: N*npoint = 82 M
+// tests per scene for SA1.  Here:
+//   1. points are counting-sorted into buckets of a hashed grid with cell edge h = 1.001*r
+//      (count -> per-scene exclusive scan -> scatter; x,y,z,index packed as float4 for 16-byte loads);
+//   2. a warp owns a centre: lanes 0..26 fetch the ranges of the 27 neighbouring cells in parallel,
+//      a warp scan flattens them into one candidate list, lanes stride over it with LDG.128, discard
+//      hash-collision strangers (the candidate's own cell must equal the probed cell, which also
+//      guarantees no point is seen twice) and apply the SAME fp32 test as the reference
+//      (d2 = fma(dz,dz,fma(dx,dx,dy*dy)) < r*r, centre minus point), so the hit SET is bit-identical;
+//   3. the reference's ORDER is restored by ranking the hits by point index (rank = number of hits with
+//      a smaller index; indices are unique), slot[rank] = index for rank < nsample, padding with the
+//      rank-0 hit.
+// The 0.1 % slack in h makes the 27-cell stencil a superset of the ball under fp32 rounding of the
+// cell coordinates.  A centre with more than BQ_CAP hits falls back to the ordered linear scan inside
+// the same kernel (rare: dense clusters), so the result is exact for every input.
+#include "common.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int BQ_CAP = 256;      // hits buffered per centre before the linear-scan fallback
+constexpr int BQ_QWARPS = 8;     // centres (warps) per CTA in the query kernel
+
+__device__ __forceinline__ uint32_t cell_hash(int ix, int iy, int iz, uint32_t mask) {
+  return ((static_cast<uint32_t>(ix) * 73856093u) ^ (static_cast<uint32_t>(iy) * 19349663u) ^
+          (static_cast<uint32_t>(iz) * 83492791u)) & mask;
+}
+__device__ __forceinline__ int cell_of(float x, float inv_h) { return static_cast<int>(floorf(x * inv_h)); }
+
+__global__ void bq_count_kernel(int n, float inv_h, uint32_t mask, const float* __restrict__ xyz,
+                                int* __restrict__ cnt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int scene = blockIdx.y;
+  const float* p = xyz + (static_cast<size_t>(scene) * n + k) * 3;
+  const uint32_t bkt = cell_hash(cell_of(__ldg(p), inv_h), cell_of(__ldg(p + 1), inv_h), cell_of(__ldg(p + 2), inv_h), mask);
+  atomicAdd(cnt + static_cast<size_t>(scene) * (mask + 2) + bkt, 1);
+}
+
+// one CTA per scene: exclusive scan of the T bucket counts in place (start[T] = n), cursor = start
+__global__ void __launch_bounds__(1024) bq_scan_kernel(int n, uint32_t T, int* __restrict__ start,
+                                                        int* __restrict__ cursor) {
+  __shared__ int warp_sum[32];
+  const int scene = blockIdx.x;
+  int* s = start + static_cast<size_t>(scene) * (T + 1);
+  int* c = cursor + static_cast<size_t>(scene) * T;
+  const int per = T / 1024;
+  const int base = threadIdx.x * per;
+  int local = 0;
+  for (int i = 0; i < per; ++i) local += s[base + i];
+  int incl = local;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    warp_sum[lane] = w;
+  }
+  __syncthreads();
+  int run = incl - local + (warp ? warp_sum[warp - 1] : 0);
+  for (int i = 0; i < per; ++i) {
+    const int v = s[base + i];
+    s[base + i] = run;
+    c[base + i] = run;
+    run += v;
+  }
+  if (threadIdx.x == 1023) s[T] = n;
+}
+
+__global__ void bq_scatter_kernel(int n, float inv_h, uint32_t mask, const float* __restrict__ xyz,
+                                  int* __restrict__ cursor, float4* __restrict__ sorted) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int scene = blockIdx.y;
+  const float* p = xyz + (static_cast<size_t>(scene) * n + k) * 3;
+  const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+  const uint32_t bkt = cell_hash(cell_of(x, inv_h), cell_of(y, inv_h), cell_of(z, inv_h), mask);
+  const int pos = atomicAdd(cursor + static_cast<size_t>(scene) * (mask + 1) + bkt, 1);
+  sorted[static_cast<size_t>(scene) * n + pos] = make_float4(x, y, z, __int_as_float(k));
+}
+
+__global__ void __launch_bounds__(BQ_QWARPS * 32)
+bq_query_kernel(int n, int m, float radius2, float inv_h, uint32_t mask, int nsample,
+                const float* __restrict__ new_xyz, const float* __restrict__ xyz, const int* __restrict__ start,
+                const float4* __restrict__ sorted, int* __restrict__ idx) {
+  __shared__ int s_begin[BQ_QWARPS][27], s_off[BQ_QWARPS][28];
+  __shared__ int s_hits[BQ_QWARPS][BQ_CAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int scene = blockIdx.y;
+  const int j = blockIdx.x * BQ_QWARPS + warp;
+  if (j >= m) return;  // warp-uniform
+  const float* c = new_xyz + (static_cast<size_t>(scene) * m + j) * 3;
+  const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
+  const int* st = start + static_cast<size_t>(scene) * (mask + 2);
+  const float4* pts = sorted + static_cast<size_t>(scene) * n;
+  int* row = idx + (static_cast<size_t>(scene) * m + j) * nsample;
+  const int bx = cell_of(cx, inv_h), by = cell_of(cy, inv_h), bz = cell_of(cz, inv_h);
+
+  // lanes 0..26: range of one neighbouring cell each
+  int begin = 0, count = 0;
+  if (lane < 27) {
+    const uint32_t bkt = cell_hash(bx + lane % 3 - 1, by + (lane / 3) % 3 - 1, bz + lane / 9 - 1, mask);
+    begin = __ldg(st + bkt);
+    count = __ldg(st + bkt + 1) - begin;
+  }
+  int incl = count;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 26);
+  if (lane < 27) { s_begin[warp][lane] = begin; s_off[warp][lane] = incl - count; }
+  if (lane == 27) s_off[warp][27] = total;
+  __syncwarp();
+
+  const uint32_t lt = (1u << lane) - 1u;
+  int nhit = 0;
+  for (int q0 = 0; q0 < total; q0 += 32) {
+    const int q = q0 + lane;
+    bool hit = false;
+    int pidx = 0;
+    if (q < total) {
+      // which of the 27 ranges holds candidate q: binary search over the exclusive offsets
+      int lo = 0, hi = 26;
+#pragma unroll
+      for (int it = 0; it < 5; ++it) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_off[warp][mid] <= q) lo = mid; else hi = mid - 1;
+      }
+      const float4 p = __ldg(pts + s_begin[warp][lo] + (q - s_off[warp][lo]));
+      // the candidate must live in the probed cell: drops hash-collision strangers and guarantees
+      // that a point reachable through two colliding cells is counted once
+      const bool mine = cell_of(p.x, inv_h) == bx + lo % 3 - 1 && cell_of(p.y, inv_h) == by + (lo / 3) % 3 - 1 &&
+                        cell_of(p.z, inv_h) == bz + lo / 9 - 1;
+      hit = mine && (sqdist3(cx - p.x, cy - p.y, cz - p.z) < radius2);
+      pidx = __float_as_int(p.w);
+    }
+    const uint32_t mk = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int pos = nhit + __popc(mk & lt);
+      if (pos < BQ_CAP) s_hits[warp][pos] = pidx;
+    }
+    nhit += __popc(mk);
+  }
+  __syncwarp();
+
+  if (nhit == 0) {
+    for (int s = lane; s < nsample; s += 32) row[s] = 0;  // empty ball: zeros (ball_query.cpp:24-26)
+    return;
+  }
+  if (nhit <= BQ_CAP) {
+    // rank the hits by point index: slot[rank] = index, padding with the rank-0 hit
+    int first = 0x7fffffff;
+    for (int i = lane; i < nhit; i += 32) {
+      const int mine = s_hits[warp][i];
+      int rank = 0;
+      for (int t = 0; t < nhit; ++t) rank += (s_hits[warp][t] < mine) ? 1 : 0;
+      if (rank < nsample) row[rank] = mine;
+      if (rank == 0) first = mine;
+    }
+    first = __reduce_min_sync(0xffffffffu, first);
+    for (int s = nhit + lane; s < nsample; s += 32) row[s] = first;
+    return;
+  }
+  // ---- overflow: ordered linear scan of the whole scene for this centre (exact, rare) -----------
+  const float* P = xyz + static_cast<size_t>(scene) * n * 3;
+  int cnt = 0, first = 0;
+  for (int base = 0; base < n && cnt < nsample; base += 32) {
+    const int k = base + lane;
+    bool hit = false;
+    if (k < n) hit = sqdist3(cx - __ldg(P + 3 * k), cy - __ldg(P + 3 * k + 1), cz - __ldg(P + 3 * k + 2)) < radius2;
+    const uint32_t mk = __ballot_sync(0xffffffffu, hit);
+    if (mk) {
+      if (cnt == 0) first = base + __ffs(mk) - 1;
+      const int pos = cnt + __popc(mk & lt);
+      if (hit && pos < nsample) row[pos] = k;
+      cnt += __popc(mk);
+    }
+  }
+  for (int s = min(cnt, nsample) + lane; s < nsample; s += 32) row[s] = first;
+}
+
+}  // namespace
+
+// Called by pn2_ball_query (search.cu) for large clouds.  Workspace comes from the stream-ordered
+// allocator, so the call stays asynchronous, stateless and re-entrant like the reference launcher.
+int ball_query_grid(int b, int n, int m, float radius, int nsample, const float* new_xyz, const float* xyz,
+                    int* idx, cudaStream_t s) {
+  const uint32_t T = n <= 131072 ? 65536u : 262144u;
+  const uint32_t mask = T - 1;
+  const float h = fabsf(radius) * 1.001f;
+  const float inv_h = 1.0f / h;
+  const float radius2 = radius * radius;
+  const size_t start_bytes = static_cast<size_t>(b) * (T + 1) * sizeof(int);
+  const size_t cursor_bytes = static_cast<size_t>(b) * T * sizeof(int);
+  const size_t sorted_off = (start_bytes + cursor_bytes + 255) & ~static_cast<size_t>(255);
+  const size_t bytes = sorted_off + static_cast<size_t>(b) * n * sizeof(float4);
+  uint8_t* ws = nullptr;
+  PN2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), bytes, s));
+  int* start = reinterpret_cast<int*>(ws);
+  int* cursor = reinterpret_cast<int*>(ws + start_bytes);
+  float4* sorted = reinterpret_cast<float4*>(ws + sorted_off);
+  int rc = PN2_OK;
+  do {
+    if (cudaMemsetAsync(start, 0, start_bytes, s) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "memset"); break; }
+    dim3 gp((n + 255) / 256, b);
+    bq_count_kernel<<<gp, 256, 0, s>>>(n, inv_h, mask, xyz, start);
+    bq_scan_kernel<<<b, 1024, 0, s>>>(n, T, start, cursor);
+    bq_scatter_kernel<<<gp, 256, 0, s>>>(n, inv_h, mask, xyz, cursor, sorted);
+    dim3 gq((m + BQ_QWARPS - 1) / BQ_QWARPS, b);
+    bq_query_kernel<<<gq, BQ_QWARPS * 32, 0, s>>>(n, m, radius2, inv_h, mask, nsample, new_xyz, xyz, start, sorted, idx);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "ball_query_grid kernels");
+  } while (0);
+  cudaFreeAsync(ws, s);
+  return rc;
+}
+
+}  // namespace pn2

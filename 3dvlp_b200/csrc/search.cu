@@ -10,6 +10,8 @@
 //
 // three_nn replaces three_nn_kernel (interpolate_gpu.cu:14-64): thread per unknown point, the known
 // set staged through shared memory in tiles, same strict-`<` cascade so ties keep the earlier index.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pn2 {
@@ -119,6 +121,10 @@ three_nn_kernel(int n, int m, const float* __restrict__ unknown, const float* __
 }
 
 }  // namespace
+
+int ball_query_grid(int b, int n, int m, float radius, int nsample, const float* new_xyz, const float* xyz,
+                    int* idx, cudaStream_t s);  // ball_query_grid.cu
+
 }  // namespace pn2
 
 extern "C" int pn2_ball_query(int b, int n, int m, float radius, int nsample, const float* new_xyz,
@@ -128,6 +134,11 @@ extern "C" int pn2_ball_query(int b, int n, int m, float radius, int nsample, co
   PN2_REQUIRE(n >= 0 && new_xyz && idx && (xyz || n == 0), "ball_query: bad arguments");
   PN2_REQUIRE(b <= 65535, "ball_query: batch %d exceeds the grid limit", b);
   const float radius2 = radius * radius;  // fp32 product, ball_query_gpu.cu:27
+  // large clouds: hashed-grid search (identical output, ~100x fewer distance tests); PN2_BQ_GRID=0
+  // forces the linear scan
+  static const bool use_grid = !(getenv("PN2_BQ_GRID") && atoi(getenv("PN2_BQ_GRID")) == 0);
+  if (use_grid && n >= 4096 && radius2 > 0.f && std::isfinite(radius) && fabsf(radius) > 1e-6f)
+    return ball_query_grid(b, n, m, radius, nsample, new_xyz, xyz, idx, as_stream(stream));
   const int per_cta = BQ_CPW * BQ_WARPS;
   dim3 grid((m + per_cta - 1) / per_cta, b);
   ball_query_kernel<<<grid, BQ_WARPS * 32, 0, as_stream(stream)>>>(n, m, radius2, nsample, new_xyz, xyz, idx);

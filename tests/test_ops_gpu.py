@@ -90,6 +90,37 @@ def test_ball_query_bit_exact(pkg, oracle, cuda, n, m, r, ns):
     assert want[:, 0].eq(0).all()
 
 
+@pytest.mark.parametrize("n,m,r,ns", [(6000, 129, 5.0, 16), (20000, 700, 0.2, 64), (9000, 300, 0.05, 8),
+                                      (5000, 200, 0.6, 32)])
+def test_ball_query_grid_path_bit_exact(pkg, oracle, cuda, n, m, r, ns):
+    """n >= 4096 takes the hashed-grid search: same hit set, order restored by index rank; balls with
+    more than 256 hits (r = 5: every point) use the in-kernel ordered linear scan."""
+    x = cloud(150 + n, 2, n, extent=1.5, dup_frac=0.2, origin_pts=3)[..., :3].contiguous()
+    x[:, : n // 20] = x[:, :1] + 0.01 * torch.randn(2, n // 20, 3, generator=torch.Generator().manual_seed(n))
+    c = x[:, torch.randperm(n, generator=torch.Generator().manual_seed(n))[:m]].contiguous()
+    c[:, 0] = 50.0      # empty ball
+    c[:, 1] = x[:, 0]   # centre inside the dense cluster: > 256 hits
+    want = oracle.ext.ball_query(c, x, r, ns)
+    got = pkg._ext.ball_query(c.to(cuda), x.to(cuda), r, ns)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_ball_query_grid_scene_40k(pkg, oracle, cuda):
+    import importlib
+    syn = importlib.import_module("3dvlp_b200.synthetic")
+    x = syn.make_batch(2, 2, 40000, 0).contiguous()  # seed 1002 has 16k duplicate points
+    inds = oracle.ext.furthest_point_sampling(x, 2048)
+    c = torch.gather(x, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    want = oracle.ext.ball_query(c, x, 0.2, 64)
+    got = pkg._ext.ball_query(c.to(cuda), x.to(cuda), 0.2, 64)
+    assert torch.equal(got.cpu(), want)
+    # negative coordinates / far-away scene offsets hash correctly
+    off = torch.tensor([-37.5, 12.25, -3.0])
+    got2 = pkg._ext.ball_query((c + off).to(cuda), (x + off).to(cuda), 0.2, 64)
+    want2 = oracle.ext.ball_query((c + off).contiguous(), (x + off).contiguous(), 0.2, 64)
+    assert torch.equal(got2.cpu(), want2)
+
+
 def test_ball_query_boundary_is_strict(pkg, oracle, cuda):
     xyz = torch.tensor([[[0.0, 0, 0], [0.1, 0, 0], [0.2, 0, 0], [5.0, 5, 5], [0.05, 0, 0], [0.3, 0, 0]]])
     centres = torch.tensor([[[0.0, 0, 0], [9.0, 9, 9], [0.25, 0, 0]]])
