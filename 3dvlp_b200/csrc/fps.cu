@@ -44,7 +44,7 @@ namespace pn2 {
 namespace {
 #endif
 
-constexpr int KMAX = 8;      // samples accepted per exchange round at most
+constexpr int KMAX = 16;     // samples accepted per exchange round at most
 constexpr int MAXC = 16;     // largest cluster
 
 struct FpsArgs {
@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(THREADS, 1) fps_kernel(const FpsArgs a) {
   constexpr int NW = THREADS / 32;
   __shared__ uint2 w_vk[NW];                      // warp record: value bits, key
   __shared__ float4 w_xyz[NW];                    // x, y, z, second
-  __shared__ __align__(16) uint4 cand[2][MAXC];   // {value bits, key32, x, y}
-  __shared__ __align__(8) uint2 cand_zs[2][MAXC]; // {z, second}
+  __shared__ __align__(16) uint4 cand[2][32];     // {value bits, key32, x, y}, slot = rank * T + t
+  __shared__ __align__(8) uint2 cand_zs[2][32];   // {z, CTA bound}
   __shared__ __align__(8) uint64_t mbar[2];
   __shared__ Centres ctr;
 
@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(THREADS, 1) fps_kernel(const FpsArgs a) {
   uint32_t round = 0;   // exchange rounds done (mbarrier parity bookkeeping)
   while (j < m) {
     const uint32_t par = round & 1u;
-    if (CLUSTERED && tid == 0) mbar_arrive_expect_tx(&mbar[par], static_cast<uint32_t>(csize) * 24u);
+    if (CLUSTERED && tid == 0)
+      mbar_arrive_expect_tx(&mbar[par], static_cast<uint32_t>(csize * min(3, 32 / csize)) * 24u);
 
     // ---- A: apply the centres accepted last round; thread-local best and second --------------
     const int kc = ctr.count;
@@ -220,25 +221,48 @@ __global__ void __launch_bounds__(THREADS, 1) fps_kernel(const FpsArgs a) {
         cv = static_cast<int>(r.x); ck = r.y; cx = w.x; cy = w.y; cz = w.z; csec = __float_as_int(w.w);
       }
       if (CLUSTERED) {
-        // ---- C+D: reduce the CTA, post {best, second} to every peer ---------------------------
-        int rv = cv;
-        uint32_t rk = ck;
-        const int src = warp_argmax(rv, rk);
-        const int cta_sec = __reduce_max_sync(0xffffffffu, lane == src ? csec : cv);
-        const float sx = __shfl_sync(0xffffffffu, cx, src), sy = __shfl_sync(0xffffffffu, cy, src),
-                    sz = __shfl_sync(0xffffffffu, cz, src);
-        if (lane < csize) {
-          const uint32_t rbar = mapa_u32(smem_u32(&mbar[par]), lane);
-          st_async_v4(mapa_u32(smem_u32(&cand[par][rank]), lane), static_cast<uint32_t>(rv), rk,
+        // ---- C+D: the CTA's top-T warp records (T = 32 / cluster size, at most 3) go to every peer,
+        // together with the CTA bound = best value among everything the CTA does NOT report.  More
+        // candidates per exchange -> longer accepted batches -> fewer dependent exchange rounds.
+        const int T = min(3, 32 / csize);
+        int rem = cv;                       // bests still unreported
+        int tv[3] = {INT_MIN, INT_MIN, INT_MIN};
+        uint32_t tk[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+        float tx[3] = {0.f, 0.f, 0.f}, ty[3] = {0.f, 0.f, 0.f}, tz[3] = {0.f, 0.f, 0.f};
+        bool taken = false;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          if (t < T) {
+            int rv = rem;
+            uint32_t rk = ck;
+            const int src = warp_argmax(rv, rk);
+            tv[t] = rv; tk[t] = rk;
+            tx[t] = __shfl_sync(0xffffffffu, cx, src); ty[t] = __shfl_sync(0xffffffffu, cy, src);
+            tz[t] = __shfl_sync(0xffffffffu, cz, src);
+            if (lane == src) { rem = INT_MIN; taken = true; }
+          }
+        }
+        // reported warps contribute their "second", the others their (unreported) best
+        const int cta_sec = __reduce_max_sync(0xffffffffu, taken ? csec : cv);
+        if (lane < csize * T) {
+          const int peer = lane / T, t = lane - peer * T;
+          const int sv = t == 0 ? tv[0] : (t == 1 ? tv[1] : tv[2]);
+          const uint32_t sk = t == 0 ? tk[0] : (t == 1 ? tk[1] : tk[2]);
+          const float sx = t == 0 ? tx[0] : (t == 1 ? tx[1] : tx[2]);
+          const float sy = t == 0 ? ty[0] : (t == 1 ? ty[1] : ty[2]);
+          const float sz = t == 0 ? tz[0] : (t == 1 ? tz[1] : tz[2]);
+          const uint32_t rbar = mapa_u32(smem_u32(&mbar[par]), peer);
+          const uint32_t slot = rank * T + t;
+          st_async_v4(mapa_u32(smem_u32(&cand[par][slot]), peer), static_cast<uint32_t>(sv), sk,
                       __float_as_uint(sx), __float_as_uint(sy), rbar);
-          st_async_v2(mapa_u32(smem_u32(&cand_zs[par][rank]), lane), __float_as_uint(sz),
+          st_async_v2(mapa_u32(smem_u32(&cand_zs[par][slot]), peer), __float_as_uint(sz),
                       static_cast<uint32_t>(cta_sec), rbar);
         }
         PN2_T(3)
         ok = mbar_wait(&mbar[par], (round >> 1) & 1u);
         PN2_T(4)
         cv = INT_MIN; ck = 0xffffffffu; csec = INT_MIN;
-        if (ok && lane < csize) {
+        if (ok && lane < csize * T) {
           const uint4 c = cand[par][lane];
           const uint2 zs = cand_zs[par][lane];
           cv = static_cast<int>(c.x); ck = c.y; cx = __uint_as_float(c.z); cy = __uint_as_float(c.w);
