@@ -4,6 +4,7 @@ Drop-in for /root/reference/models/base_module/backbone_module.py:11-135 -- same
 argument, the same hard-coded layer hyper-parameters (:29-67), the same ``data_dict`` keys in and
 out, and the same parameter names (96 state-dict entries) so reference checkpoints load.
 """
+import torch
 import torch.nn as nn
 
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
@@ -32,7 +33,13 @@ class Pointnet2Backbone(nn.Module):
     def forward(self, data_dict):
         """data_dict['point_clouds']: (B, N, 3 + input_feature_dim) fp32, rows (x, y, z, features...).
         Adds sa{1,2}_{inds,xyz,features}, sa{3,4}_{xyz,features}, fp2_{features,xyz,inds}."""
-        xyz, features = self._break_up_pc(data_dict["point_clouds"])
+        pc = data_dict["point_clouds"]
+        if not self.training and not torch.is_grad_enabled() and pc.is_cuda:
+            from . import fused
+            out = fused.backbone_forward(self, data_dict)  # sampling chain on a side stream
+            if out is not None:
+                return out
+        xyz, features = self._break_up_pc(pc)
 
         xyz, features, fps_inds = self.sa1(xyz, features)
         data_dict['sa1_inds'], data_dict['sa1_xyz'], data_dict['sa1_features'] = fps_inds, xyz, features

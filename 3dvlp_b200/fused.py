@@ -88,7 +88,8 @@ class _SaPlan:
         return c1 in (64, 128) and c2 in (64, 128) and c3 in (128, 256)
 
 
-def sa_forward(module, xyz, features, inds):
+def _sa_plan(module):
+    """The cached folded/packed parameters of an SA module, or None if it cannot run fused."""
     if module._fused is False:
         return None
     if module._fused is None or module._fused.key != _version_key(module):
@@ -96,20 +97,23 @@ def sa_forward(module, xyz, features, inds):
             module._fused = False
             return None
         module._fused = _SaPlan(module)
-    plan = module._fused
-    c_feat = 0 if features is None else features.shape[1]
-    if c_feat != plan.c_in or xyz.dtype != torch.float32:
-        return None
-    xyz = xyz.contiguous()
+    return module._fused
+
+
+def sa_sample(module, xyz, inds=None):
+    """FPS (+ the xyz gather) of an SA layer -- geometry only, independent of the features."""
+    if inds is None:
+        return _ext.furthest_point_sampling_gather(xyz, module.npoint)
+    new_xyz = torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    return inds, new_xyz
+
+
+def sa_features(module, plan, xyz, features, new_xyz):
+    """Ball query + (wide inputs: per-point GEMM) + the fused grouping/MLP/max-pool kernel."""
     b, n = xyz.shape[0], xyz.shape[1]
     dev = xyz.device
-
-    if inds is None:
-        inds, new_xyz = _ext.furthest_point_sampling_gather(xyz, module.npoint)
-    else:
-        new_xyz = torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    c_feat = 0 if features is None else features.shape[1]
     idx = _ext.ball_query(new_xyz, xyz, module.radius, module.nsample)
-
     g = None
     feat = None
     if plan.direct:
@@ -120,7 +124,6 @@ def sa_forward(module, xyz, features, inds):
         if rows is None or rows.shape != (b * n, plan.w1f.kpad) or rows.device != dev:
             rows = tcm.pack_rows(features.contiguous().float(), plan.w1f.kpad)
         g = tcm.linear(rows, plan.w1f, None, relu=False, out="f32")
-
     out_cm = torch.empty(b, plan.c3, module.npoint, device=dev, dtype=torch.float32)
     out_pm = torch.empty(b * module.npoint, plan.c3, device=dev, dtype=torch.bfloat16)
     radius_div = float(module.radius) if module.normalize_xyz else 1.0
@@ -129,7 +132,85 @@ def sa_forward(module, xyz, features, inds):
            plan.c3, L.ptr(plan.w1), L.ptr(plan.b1), L.ptr(plan.w2p.data), L.ptr(plan.b2), L.ptr(plan.w3p.data),
            L.ptr(plan.b3), L.ptr(out_cm), L.ptr(out_pm), L.stream_of(xyz), device=dev)
     out_cm._pn2_rows = out_pm  # bf16 point-major twin: the next SA layer's GEMM operand, no repack
-    return new_xyz, out_cm, inds
+    return out_cm
+
+
+def sa_forward(module, xyz, features, inds):
+    plan = _sa_plan(module)
+    if plan is None:
+        return None
+    c_feat = 0 if features is None else features.shape[1]
+    if c_feat != plan.c_in or xyz.dtype != torch.float32:
+        return None
+    xyz = xyz.contiguous()
+    inds, new_xyz = sa_sample(module, xyz, inds)
+    return new_xyz, sa_features(module, plan, xyz, features, new_xyz), inds
+
+
+_side_streams = {}
+
+
+def backbone_forward(bb, data_dict):
+    """Whole-backbone fast path (eval, no grad).  The sampling chain FPS1 -> FPS2 -> FPS3 -> FPS4 only
+    needs coordinates, never features, and it is the latency-bound part of the step (each FPS is a
+    serial chain that occupies a few SMs).  It therefore runs on a SIDE stream, and the feature path
+    (ball query, grouped MLP, FP layers) of layer i runs on the caller's stream as soon as FPS i has
+    finished -- underneath FPS i+1.  Same kernels, same results, shorter critical path.
+    Returns None when any layer cannot run fused (the caller then goes module by module)."""
+    import os
+    if os.environ.get("PN2_TWO_STREAM", "1") == "0":
+        return None
+    sas = (bb.sa1, bb.sa2, bb.sa3, bb.sa4)
+    plans = []
+    for sa in sas:
+        if not sa._can_fuse(data_dict["point_clouds"], None):
+            return None
+        plan = _sa_plan(sa)
+        if plan is None:
+            return None
+        plans.append(plan)
+    pc = data_dict["point_clouds"]
+    if pc.dtype != torch.float32 or pc.size(-1) - 3 != plans[0].c_in:
+        return None
+    xyz, features = bb._break_up_pc(pc)
+    dev = xyz.device
+    main = torch.cuda.current_stream(dev)
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(main)
+    geo = []
+    with torch.cuda.stream(side):
+        x = xyz
+        for sa in sas:
+            inds, new_xyz = sa_sample(sa, x)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            geo.append((inds, new_xyz, ev))
+            x = new_xyz
+    x, f = xyz, features
+    names = ("sa1", "sa2", "sa3", "sa4")
+    for name, sa, plan, (inds, new_xyz, ev) in zip(names, sas, plans, geo):
+        main.wait_event(ev)
+        inds.record_stream(main)
+        new_xyz.record_stream(main)
+        c_feat = 0 if f is None else f.shape[1]
+        if c_feat != plan.c_in:
+            main.wait_stream(side)
+            return None
+        f = sa_features(sa, plan, x, f, new_xyz)
+        x = new_xyz
+        data_dict[name + "_xyz"] = x
+        data_dict[name + "_features"] = f
+        if name in ("sa1", "sa2"):
+            data_dict[name + "_inds"] = inds
+    feats = bb.fp1(data_dict["sa3_xyz"], data_dict["sa4_xyz"], data_dict["sa3_features"], data_dict["sa4_features"])
+    feats = bb.fp2(data_dict["sa2_xyz"], data_dict["sa3_xyz"], data_dict["sa2_features"], feats)
+    data_dict["fp2_features"] = feats
+    data_dict["fp2_xyz"] = data_dict["sa2_xyz"]
+    num_seed = data_dict["fp2_xyz"].shape[1]
+    data_dict["fp2_inds"] = data_dict["sa1_inds"][:, 0:num_seed]
+    return data_dict
 
 
 class _FpPlan:
