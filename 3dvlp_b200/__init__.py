@@ -17,10 +17,11 @@ import sys as _sys
 from . import _lib  # noqa: F401
 from . import _ext, backbone, nn_distance as _nn_distance_mod, pointnet2_modules, pointnet2_utils, pytorch_utils  # noqa: F401
 from .backbone import Pointnet2Backbone  # noqa: F401
+from .graph import GraphedBackbone  # noqa: F401
 from .nn_distance import huber_loss, knn_distance, nn_distance  # noqa: F401
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes  # noqa: F401
 
-__all__ = ["Pointnet2Backbone", "PointnetSAModuleVotes", "PointnetFPModule", "nn_distance", "huber_loss",
+__all__ = ["Pointnet2Backbone", "GraphedBackbone", "PointnetSAModuleVotes", "PointnetFPModule", "nn_distance", "huber_loss",
            "knn_distance", "pointnet2_utils", "pointnet2_modules", "pytorch_utils", "install_dropin"]
 
 

@@ -89,7 +89,9 @@ struct Centres {          // published by warp 0 each round
 };
 
 template <int P, int THREADS, bool CLUSTERED>
-__global__ void __launch_bounds__(THREADS, 1) fps_kernel(const FpsArgs a) {
+// P <= 5 fits 64 registers per thread: two CTAs (of different clusters / scenes) share an SM, so the
+// idle issue slots of one scene's serial phase run another scene's bulk update.
+__global__ void __launch_bounds__(THREADS, (P <= 5 && THREADS <= 512) ? 2 : 1) fps_kernel(const FpsArgs a) {
   constexpr int NW = THREADS / 32;
   __shared__ uint2 w_vk[NW];                      // warp record: value bits, key
   __shared__ float4 w_xyz[NW];                    // x, y, z, second

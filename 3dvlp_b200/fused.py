@@ -178,6 +178,7 @@ def backbone_forward(bb, data_dict):
     side = _side_streams.get(dev)
     if side is None:
         side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    capturing = torch.cuda.is_current_stream_capturing()
     side.wait_stream(main)
     geo = []
     with torch.cuda.stream(side):
@@ -192,8 +193,9 @@ def backbone_forward(bb, data_dict):
     names = ("sa1", "sa2", "sa3", "sa4")
     for name, sa, plan, (inds, new_xyz, ev) in zip(names, sas, plans, geo):
         main.wait_event(ev)
-        inds.record_stream(main)
-        new_xyz.record_stream(main)
+        if not capturing:  # graph-private pool memory is never handed to another stream
+            inds.record_stream(main)
+            new_xyz.record_stream(main)
         c_feat = 0 if f is None else f.shape[1]
         if c_feat != plan.c_in:
             main.wait_stream(side)

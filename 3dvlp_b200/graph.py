@@ -1,0 +1,54 @@
+"""CUDA-graph replay of the eval-mode backbone.
+
+A backbone forward is ~40 short kernel launches on two streams; at 2 ms per step the Python / driver
+launch path is of the same order as the GPU work.  Shapes are static (B scenes x N points), every
+kernel is stream-ordered (the ball-query workspace comes from the stream-ordered allocator), so the
+whole forward -- including the fork/join of the sampling stream -- is captured ONCE into a CUDA graph
+and replayed per batch: one launch per step, no tracing compiler involved.
+"""
+import torch
+
+
+class GraphedBackbone:
+    """``g = GraphedBackbone(backbone, example_batch); out = g(point_clouds)``.
+
+    `example_batch` (B, N, 3+C) fp32 CUDA fixes the shapes.  ``g(pc)`` copies `pc` (device or pinned
+    host tensor) into the static input, replays the graph on the current stream and returns the dict
+    of STATIC output tensors (same keys as Pointnet2Backbone.forward); they are overwritten by the
+    next call.  Falls back to eager execution (``self.graph is None``) if capture is not possible.
+    """
+
+    def __init__(self, backbone, example_batch, warmup=3):
+        if backbone.training:
+            raise RuntimeError("GraphedBackbone needs the backbone in eval() mode")
+        if not example_batch.is_cuda or example_batch.dtype != torch.float32:
+            raise RuntimeError("CPU not supported")
+        self.backbone = backbone
+        self.static_in = example_batch.clone().contiguous()
+        self.graph = None
+        self.static_out = None
+        self.capture_error = None
+        cur = torch.cuda.current_stream(self.static_in.device)
+        s = torch.cuda.Stream(device=self.static_in.device)
+        s.wait_stream(cur)
+        with torch.no_grad(), torch.cuda.stream(s):
+            for _ in range(max(1, warmup)):  # fills every host-side cache (plans, occupancy, pools)
+                backbone({"point_clouds": self.static_in})
+        cur.wait_stream(s)
+        torch.cuda.synchronize(self.static_in.device)
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(g):
+                out = backbone({"point_clouds": self.static_in})
+            self.graph, self.static_out = g, out
+        except Exception as ex:  # pragma: no cover - depends on driver behaviour
+            self.capture_error = repr(ex)
+            torch.cuda.synchronize(self.static_in.device)
+
+    def __call__(self, point_clouds):
+        self.static_in.copy_(point_clouds, non_blocking=True)
+        if self.graph is None:
+            with torch.no_grad():
+                return self.backbone({"point_clouds": self.static_in})
+        self.graph.replay()
+        return self.static_out

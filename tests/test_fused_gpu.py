@@ -162,3 +162,25 @@ def test_backbone_fused_vs_oracle(pkg, oracle, cuda):
         err = (d[k].cpu() - want[k]).abs().max().item() / want[k].abs().max().item()
         assert err < 3e-2, (k, err)
     assert d["fp2_features"].shape == (2, 256, 1024) and d["fp2_inds"].dtype == torch.int32
+
+
+def test_graphed_backbone_replays_identically(pkg, cuda):
+    """CUDA-graph replay == eager forward, on fresh inputs copied into the static buffer."""
+    import importlib
+    from common import fill_state_dict
+    syn = importlib.import_module("3dvlp_b200.synthetic")
+    bb = pkg.Pointnet2Backbone(input_feature_dim=1)
+    fill_state_dict(bb)
+    bb = bb.to(cuda).eval()
+    a = syn.make_batch(0, 2, 9000, 1).to(cuda)   # 9000 points: cluster FPS + grid ball query
+    b2 = syn.make_batch(5, 2, 9000, 1).to(cuda)
+    g = pkg.GraphedBackbone(bb, a)
+    assert g.graph is not None, g.capture_error
+    for pc in (b2, a, b2):
+        out = g(pc)
+        torch.cuda.synchronize()
+        got = {k: out[k].clone() for k in ("sa1_inds", "sa2_inds", "fp2_inds", "fp2_xyz", "fp2_features", "sa4_features")}
+        with torch.no_grad():
+            want = bb({"point_clouds": pc.clone()})
+        for k, v in got.items():
+            assert torch.equal(v, want[k]), k
