@@ -276,47 +276,48 @@ __global__ void __launch_bounds__(THREADS, (P <= 5 && THREADS <= 512) ? 2 : 1) f
       // iteration needs: arg-max, broadcast of the winner's xyz, the candidates' update.  Lane k
       // keeps the k-th accepted record; decoding, the shared-memory publish and the global stores
       // happen once after the loop, one lane per sample.
-      const int bound = __reduce_max_sync(0xffffffffu, csec);
+      // bnd folds both acceptance conditions (value > bound and value > 0) into one compare
+      const int bnd = max(__reduce_max_sync(0xffffffffu, csec), 0);
       const int room = min(KMAX, m - j);
       int k = 0;
-      uint32_t mykey = 0;
-      int myval = -1;
-      float mx = x0, my = y0, mz = z0;
-      while (ok) {
-        const int rv = __reduce_max_sync(0xffffffffu, cv);
-        if (k > 0 && !(rv > bound && rv > 0)) break;  // int compare == float compare for values >= 0
-        uint32_t tie = __ballot_sync(0xffffffffu, cv == rv);
-        if (__popc(tie) > 1) {  // equal values: the smallest key wins (keys are unique)
-          const uint32_t kk = (cv == rv) ? ck : 0xffffffffu;
-          const uint32_t kmin = __reduce_min_sync(0xffffffffu, kk);
-          tie = __ballot_sync(0xffffffffu, kk == kmin);
-        }
-        const int src = __ffs(tie) - 1;
-        const float ax = __shfl_sync(0xffffffffu, cx, src), ay = __shfl_sync(0xffffffffu, cy, src),
-                    az = __shfl_sync(0xffffffffu, cz, src);
-        const uint32_t ak = __shfl_sync(0xffffffffu, ck, src);
-        if (lane == k) { mykey = ak; myval = rv; mx = ax; my = ay; mz = az; }
-        ++k;
-        if (k >= room || rv < 0) break;
-        // lower every candidate -- the accepted one included -- by its exact distance to the new
-        // centre: a finite point drops to 0 and can never be re-accepted in this round (rv > 0); a
-        // point with inf/NaN coordinates keeps its value (d is NaN) exactly as in the reference
-        if (cv >= 0) cv = __float_as_int(fminf(sqdist3(cx - ax, cy - ay, cz - az), __int_as_float(cv)));
-      }
-      if (ok && lane < k) {
-        int old = 0;
-        if (myval < 0) {  // no eligible point anywhere: every reference thread reports besti = 0
-          mx = x0; my = y0; mz = z0;
+      if (ok) {
+        int rv = __reduce_max_sync(0xffffffffu, cv);
+        if (rv < 0) {
+          // no eligible point anywhere: every reference thread reports besti = 0 (key of index 0 is 0)
+          if (lane == 0) ctr.c[0] = make_float4(x0, y0, z0, __uint_as_float(0u));
+          k = 1;
         } else {
-          const uint32_t row = mykey & rowmask;
-          const uint32_t vv = log2bs ? __brev(mykey & ~rowmask) : 0u;
-          old = static_cast<int>(vv + (row << log2bs));
+          for (;;) {
+            uint32_t tie = __ballot_sync(0xffffffffu, cv == rv);
+            if (tie & (tie - 1)) {  // equal values: the smallest key wins (keys are unique)
+              const uint32_t kk = (cv == rv) ? ck : 0xffffffffu;
+              const uint32_t kmin = __reduce_min_sync(0xffffffffu, kk);
+              tie = __ballot_sync(0xffffffffu, kk == kmin);
+            }
+            const int src = __ffs(tie) - 1;
+            const float ax = __shfl_sync(0xffffffffu, cx, src), ay = __shfl_sync(0xffffffffu, cy, src),
+                        az = __shfl_sync(0xffffffffu, cz, src);
+            const uint32_t ak = __shfl_sync(0xffffffffu, ck, src);
+            if (lane == 0) ctr.c[k] = make_float4(ax, ay, az, __uint_as_float(ak));  // key rides in .w
+            if (++k >= room) break;
+            // lower every candidate -- the accepted one included -- by its exact distance to the new
+            // centre: a finite point drops to 0 and can never be re-accepted in this round; a point
+            // with inf/NaN coordinates keeps its value (d is NaN) exactly as in the reference.  Lanes
+            // without a record hold -0.0f / -1.0f, which fminf leaves untouched.
+            cv = __float_as_int(fminf(sqdist3(cx - ax, cy - ay, cz - az), __int_as_float(cv)));
+            rv = __reduce_max_sync(0xffffffffu, cv);
+            if (!(rv > bnd)) break;  // int compare == float compare for values >= 0
+          }
         }
-        ctr.c[lane] = make_float4(mx, my, mz, 0.f);
-        if (rank == 0) {
-          idxs[j + lane] = old;
-          if (oxyz) { oxyz[3 * (j + lane)] = mx; oxyz[3 * (j + lane) + 1] = my; oxyz[3 * (j + lane) + 2] = mz; }
-        }
+      }
+      __syncwarp();
+      if (ok && lane < k && rank == 0) {
+        const float4 cc = ctr.c[lane];
+        const uint32_t mykey = __float_as_uint(cc.w);
+        const uint32_t row = mykey & rowmask;
+        const uint32_t vv = log2bs ? __brev(mykey & ~rowmask) : 0u;
+        idxs[j + lane] = static_cast<int>(vv + (row << log2bs));
+        if (oxyz) { oxyz[3 * (j + lane)] = cc.x; oxyz[3 * (j + lane) + 1] = cc.y; oxyz[3 * (j + lane) + 2] = cc.z; }
       }
       if (lane == 0) ctr.count = ok ? k : -1;
     }
