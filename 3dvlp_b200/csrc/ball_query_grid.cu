@@ -42,44 +42,73 @@ __global__ void bq_count_kernel(int n, float inv_h, uint32_t mask, const float* 
   atomicAdd(cnt + static_cast<size_t>(scene) * (mask + 2) + bkt, 1);
 }
 
-// one CTA per scene: exclusive scan of the T bucket counts in place (start[T] = n), cursor = start
+// one CTA per scene: exclusive scan of the T bucket counts (start[T] = n), cursor = start.
+// Coalesced: the 1024 threads sweep a group of 65 536 buckets as 16 chunks of 4096 with lane-contiguous
+// 4-element pieces; the 16 per-thread chunk sums are scanned across the block together (one shuffle
+// scan + two shared-memory hops for all 16 chunks), then the pieces are re-read and the exclusive
+// prefixes written back with the same coalesced pattern.
 __global__ void __launch_bounds__(1024) bq_scan_kernel(int n, uint32_t T, int* __restrict__ start,
                                                         int* __restrict__ cursor) {
-  __shared__ int warp_sum[32];
+  constexpr int NCH = 16;              // chunks per group
+  __shared__ int wsum[NCH][33];        // per chunk: inclusive scan of the 32 warp sums
+  __shared__ int cpre[NCH + 1];        // exclusive prefix of the chunk totals (+ group total)
   const int scene = blockIdx.x;
   int* s = start + static_cast<size_t>(scene) * (T + 1);
   int* c = cursor + static_cast<size_t>(scene) * T;
-  const int per = T / 1024;
-  const int base = threadIdx.x * per;
-  int local = 0;
-  for (int i = 0; i < per; ++i) local += s[base + i];
-  int incl = local;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int group_carry = 0;
+  for (uint32_t g0 = 0; g0 < T; g0 += NCH * 4096) {
+    int ts[NCH], inc[NCH];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) warp_sum[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    int w = warp_sum[lane];
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int* p = s + g0 + ch * 4096 + tid * 4;
+      ts[ch] = p[0] + p[1] + p[2] + p[3];
+      inc[ch] = ts[ch];
+    }
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += v;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int t = __shfl_up_sync(0xffffffffu, inc[ch], o);
+        if (lane >= o) inc[ch] += t;
+      }
     }
-    warp_sum[lane] = w;
+    if (lane == 31) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) wsum[ch][warp] = inc[ch];
+    }
+    __syncthreads();
+    if (warp < NCH) {  // warp `ch` scans the 32 warp sums of chunk `ch`
+      int w = wsum[warp][lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      wsum[warp][lane] = w;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int ch = 0; ch < NCH; ++ch) { cpre[ch] = run; run += wsum[ch][31]; }
+      cpre[NCH] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      int run = group_carry + cpre[ch] + (warp ? wsum[ch][warp - 1] : 0) + inc[ch] - ts[ch];
+      int* p = s + g0 + ch * 4096 + tid * 4;
+      int* q = c + g0 + ch * 4096 + tid * 4;
+      const int v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
+      p[0] = run; q[0] = run; run += v0;
+      p[1] = run; q[1] = run; run += v1;
+      p[2] = run; q[2] = run; run += v2;
+      p[3] = run; q[3] = run; (void)v3;
+    }
+    group_carry += cpre[NCH];
+    __syncthreads();
   }
-  __syncthreads();
-  int run = incl - local + (warp ? warp_sum[warp - 1] : 0);
-  for (int i = 0; i < per; ++i) {
-    const int v = s[base + i];
-    s[base + i] = run;
-    c[base + i] = run;
-    run += v;
-  }
-  if (threadIdx.x == 1023) s[T] = n;
+  if (tid == 0) s[T] = n;
 }
 
 __global__ void bq_scatter_kernel(int n, float inv_h, uint32_t mask, const float* __restrict__ xyz,

@@ -195,6 +195,30 @@ def reference_cuda_ext_leg(torch, pkg, model, dev_pool, steps):
             "what": "unmodified reference _ext (sm_100a build) + torch/cuDNN layers, same inputs, 1 GPU"}
 
 
+def algorithmic_work():
+    """Algorithmic bytes (HBM-bound ops) or FLOPs (tensor ops) per C-ABI call of one backbone forward on
+    8 scenes x 40 000 points, C_in = 1 -- SURVEY.md section 8(d) / BASELINE.md section 4, keyed by
+    (entry point, n-th call).  FPS / ball query / 3-NN are latency- or ALU-bound by construction; their
+    HBM fraction is reported for completeness (bound "hbm (latency-bound)")."""
+    b = SCENES_PER_GPU
+    sa = [(N_POINTS, 2048, 64, (3 + C_IN, 64, 64, 128)), (2048, 1024, 32, (131, 128, 128, 256)),
+          (1024, 512, 16, (259, 128, 128, 256)), (512, 256, 16, (259, 128, 128, 256))]
+    w = {}
+    for i, (n, m, ns, ch) in enumerate(sa):
+        w[("pn2_furthest_point_sampling_gather", i)] = ("hbm (latency-bound)", b * (12 * n + 16 * m))
+        w[("pn2_ball_query", i)] = ("hbm (latency-bound)", b * (12 * n + 12 * m + 4 * m * ns))
+        flops = 2 * b * m * ns * (ch[0] * ch[1] + ch[1] * ch[2] + ch[2] * ch[3])
+        w[("pn2_sa_group_mlp", i)] = ("tensor", flops)
+    # point-wise linears: SA2..SA4 per-point halves (K = 128 / 256 / 256), then FP1, FP2 (2 layers each)
+    lin = [(b * 2048, 128, 128), (b * 1024, 128, 256), (b * 512, 128, 256),
+           (b * 512, 256, 512), (b * 512, 256, 256), (b * 1024, 256, 512), (b * 1024, 256, 256)]
+    for i, (m, n, k) in enumerate(lin):
+        w[("pn2_linear_bf16", i)] = ("tensor", 2 * m * n * k)
+    for i, (n, m) in enumerate([(512, 256), (1024, 512)]):
+        w[("pn2_fp_prepare", i)] = ("hbm", b * (12 * (n + m) + 4 * 256 * m + 4 * 256 * n + 2 * 512 * n))
+    return w
+
+
 def per_op_profile(torch, L, model, batch, reps=5):
     """Per-C-ABI-call device time with CUDA events on the launching stream (one forward per rep)."""
     acc = {}
@@ -215,8 +239,8 @@ def per_op_profile(torch, L, model, batch, reps=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=4, help="batches in flight (graph replays on separate streams)")
@@ -339,17 +363,34 @@ def main():
         if fps_key is not None:
             t_fps = ops[fps_key] * 1e-3
             b = SCENES_PER_GPU
-            bytes_alg = b * (12 * N_POINTS + 4 * 2048 + 12 * 2048)  # xyz in, inds + new_xyz out
+            bytes_alg = b * (12 * N_POINTS + 16 * 2048)  # xyz in, inds + new_xyz out
             updates = b * N_POINTS * 2047
             ach = bytes_alg / t_fps / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+            if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+                traffic = json.load(open(tp)).get("fps_kernel_sa1_bytes_per_launch")
             roofline = {"kernel": "fps_kernel (SA1, 40000->2048)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                        "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_kind": peak_kind,
-                        "ms": ops[fps_key], "share_of_step": ops[fps_key] / step_ms,
+                        "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
+                        "ms": ops[fps_key], "share_of_forward": ops[fps_key] / sum(ops.values()),
                         "note": "FPS is latency/ALU-bound by construction (2047 dependent rounds); see alu_frac",
                         "alu_gflops": updates * 10 / t_fps / 1e9, "alu_frac": updates * 10 / t_fps / 74.5e12,
-                        "us_per_round": ops[fps_key] * 1e3 / 2047}
+                        "us_per_sample": ops[fps_key] * 1e3 / 2047}
+        work = algorithmic_work()
         for (name, k), v in sorted(ops.items(), key=lambda kv: -kv[1]):
-            roofline_ops.append({"call": name, "nth": k, "ms": round(v, 4), "share_of_step": round(v / step_ms, 4)})
+            row = {"call": name, "nth": k, "ms": round(v, 4), "share_of_forward": round(v / sum(ops.values()), 4)}
+            w = work.get((name, k))
+            if w:
+                bound, amount = w
+                if bound == "tensor":
+                    ach = amount / (v * 1e-3) / 1e12
+                    row.update({"bound": "tensor", "achieved": round(ach, 3), "unit": "TFLOP/s",
+                                "frac": round(ach / tensor_peak, 5)})
+                else:
+                    ach = amount / (v * 1e-3) / 1e9
+                    row.update({"bound": bound, "achieved": round(ach, 2), "unit": "GB/s",
+                                "frac": round(ach / hbm_peak, 5)})
+            roofline_ops.append(row)
         line = {"metric": "scenes/sec Pointnet2Backbone fwd (40k pts)", "value": value, "unit": "scenes/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
