@@ -396,6 +396,9 @@ int dispatch_p(int p, const FpsArgs& a, int b, cudaStream_t s, int* max_active) 
 #endif
 
 int* device_err_flag();  // abi.cu
+bool fps_bucket_supported(int n);  // fps_bucket.cu
+int fps_bucket_run(int b, int n, int m, int log2bs, const float* dataset, int* idxs, float* new_xyz,
+                   cudaStream_t stream);
 #ifdef PN2_FPS_TIMING
 long long* fps_dbg_ptr = nullptr;
 #endif
@@ -435,6 +438,10 @@ int fps_run(int b, int n, int m, const float* dataset, int* idxs, float* new_xyz
   a.dbg = fps_dbg_ptr;
 #endif
   PN2_REQUIRE(a.err != nullptr, "furthest_point_sampling: cannot allocate the device error flag");
+
+  // mid-size scenes (SA1 at 40k points): single-CTA bucketed kernel with spatial pruning
+  static const int use_bucket = env_int("PN2_FPS_BUCKET", 1);
+  if (use_bucket && fps_bucket_supported(n)) return fps_bucket_run(b, n, m, log2bs, dataset, idxs, new_xyz, stream);
 
   static const int force_cluster = env_int("PN2_FPS_CLUSTER", 0);
   static const int force_threads = env_int("PN2_FPS_THREADS", 0);

@@ -1,0 +1,456 @@
+// Bucketed furthest point sampling: ONE CTA per scene, exact, with spatial pruning.
+//
+// csrc/fps.cu spreads a scene over a 16-CTA cluster and touches all N points for every accepted sample.
+// Late in a run almost none of those updates change anything: a new sample only lowers the running
+// minimum `temp` of points closer to it than sqrt(temp).  This kernel exploits that while keeping the
+// reference's output bit for bit (same fp32 distance expression, same (temp, key) arg-max as
+// sampling_gpu.cu:75-178 -- see the header of fps.cu for the key):
+//
+//   prologue  the CTA counting-sorts its scene into a coarse Morton grid (shared-memory histogram,
+//             no extra launches) and cuts the sorted sequence into BUCKETS of 64 consecutive points
+//             (x, y, z, original index as float4 in a global scratch that stays L2-resident);
+//             running minima live in shared memory (4 B/point), buckets carry {max temp, key and
+//             xyz of that point, second-largest temp}; 32 consecutive buckets form a GROUP = one warp.
+//   round     K centres were accepted in the previous round (batched acceptance as in fps.cu):
+//     1. prune  lane c of every warp tests centre c against the warp's group box; only buckets of hit
+//               groups test their own box.  A (bucket, centre) pair is dropped iff
+//               0.9999 * d2(centre, box) >= max temp of the bucket: no point of the bucket can change.
+//     2. update the surviving (bucket, centre-mask) items are spread over the 32 warps: lane = point,
+//               16-byte coalesced load, fminf chain, redux.sync for the bucket's new max / key / second.
+//     3. select thread = bucket, warp = group: redux arg-max -> one candidate per warp (32 candidates)
+//               plus the bound that dominates every non-candidate.
+//     4. accept warp 0 replays greedy FPS on the 32 candidates (exact; fps.cu header) and publishes
+//               up to KMAX new centres.
+// Work per sample drops from N distance updates to ~0.5 k, and a scene needs 1 SM instead of 16, so a
+// batch no longer monopolises the GPU: other kernels and other batches run beside it.
+#include "common.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int FB_THREADS = 1024;
+constexpr int FB_WARPS = 32;
+constexpr int FB_KMAX = 16;       // centres accepted per round at most
+constexpr int FB_CELLS = 8192;    // sort grid: 32 x 32 (Morton) x 8
+constexpr int FB_BK = 64;         // points per bucket (two per lane)
+
+struct FbArgs {
+  const float* xyz;   // (b, n, 3)
+  float4* sorted;     // (b, npad) scratch
+  int* idxs;          // (b, m)
+  float* new_xyz;     // (b, m, 3) or nullptr
+  int n, m, log2bs, nb, npad;
+};
+
+struct Box { float lx, ly, lz, hx, hy, hz; };
+
+__device__ __forceinline__ float box_d2(const Box& b, float x, float y, float z) {
+  const float dx = fmaxf(fmaxf(b.lx - x, x - b.hx), 0.f);
+  const float dy = fmaxf(fmaxf(b.ly - y, y - b.hy), 0.f);
+  const float dz = fmaxf(fmaxf(b.lz - z, z - b.hz), 0.f);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+__device__ __forceinline__ uint32_t part1by1(uint32_t v) {  // spread the low 5 bits
+  v &= 0x1fu;
+  v = (v | (v << 4)) & 0x0f0fu;   // not needed beyond 5 bits but harmless
+  v = (v | (v << 2)) & 0x3333u;
+  v = (v | (v << 1)) & 0x5555u;
+  return v;
+}
+
+__device__ __forceinline__ int warp_argmax2(int& v, uint32_t& k) {
+  const int vmax = __reduce_max_sync(0xffffffffu, v);
+  const uint32_t kk = (v == vmax) ? k : 0xffffffffu;
+  const uint32_t kmin = __reduce_min_sync(0xffffffffu, kk);
+  const uint32_t win = __ballot_sync(0xffffffffu, kk == kmin && v == vmax);
+  v = vmax;
+  k = kmin;
+  return __ffs(win) - 1;
+}
+
+__global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ float4 ctr[FB_KMAX];     // accepted centres (x, y, z, key bits)
+  __shared__ int ctr_count;
+  __shared__ int nwork;
+  __shared__ uint2 w_vk[FB_WARPS];
+  __shared__ float4 w_xyz[FB_WARPS];
+  __shared__ float red[FB_WARPS][6];
+  __shared__ float s_org[3], s_scale[3];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int scene = blockIdx.x;
+  const int n = a.n, m = a.m, log2bs = a.log2bs, nb = a.nb, npad = a.npad;
+  const float* __restrict__ xyz = a.xyz + static_cast<size_t>(scene) * n * 3;
+  float4* __restrict__ sorted = a.sorted + static_cast<size_t>(scene) * npad;
+  int* __restrict__ idxs = a.idxs + static_cast<size_t>(scene) * m;
+  float* __restrict__ oxyz = a.new_xyz ? a.new_xyz + static_cast<size_t>(scene) * m * 3 : nullptr;
+
+  float* temps = reinterpret_cast<float*>(smem_raw);                 // npad
+  float4* bb_a = reinterpret_cast<float4*>(temps + npad);            // nb: {max temp, key bits, x, y}
+  float2* bb_b = reinterpret_cast<float2*>(bb_a + nb);               // nb: {z, second temp}
+  uint32_t* work = reinterpret_cast<uint32_t*>(bb_b + nb);           // nb: bucket | centre mask << 16
+  int* hist = reinterpret_cast<int*>(smem_raw);                      // aliases temps during the sort
+  int* cursor = hist + FB_CELLS;
+
+  const uint32_t bsmask = (1u << log2bs) - 1u;
+  const uint32_t rowmask = log2bs ? ((1u << (32 - log2bs)) - 1u) : 0xffffffffu;
+  const uint32_t lt = (1u << lane) - 1u;
+  const float x0 = __ldg(xyz), y0 = __ldg(xyz + 1), z0 = __ldg(xyz + 2);
+#ifdef PN2_FB_DEBUG
+  const long long dbg_t0 = clock64();
+#endif
+
+  // ================= prologue: counting sort into the coarse Morton grid ==========================
+  {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int k = tid; k < n; k += FB_THREADS) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float v = __ldg(xyz + 3 * k + d);
+        if (fabsf(v) <= 3.0e38f) { lo[d] = fminf(lo[d], v); hi[d] = fmaxf(hi[d], v); }  // finite only
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+        hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+      }
+      if (lane == 0) { red[warp][d] = lo[d]; red[warp][3 + d] = hi[d]; }
+    }
+    for (int i = tid; i < 2 * FB_CELLS; i += FB_THREADS) hist[i] = 0;
+    __syncthreads();
+    if (tid < 3) {
+      float l = INFINITY, h = -INFINITY;
+      for (int w = 0; w < FB_WARPS; ++w) { l = fminf(l, red[w][tid]); h = fmaxf(h, red[w][3 + tid]); }
+      if (!(h >= l)) { l = 0.f; h = 1.f; }
+      const float cells = tid == 2 ? 8.f : 32.f;
+      s_org[tid] = l;
+      s_scale[tid] = cells / fmaxf((h - l) * 1.0001f, 1e-20f);
+    }
+    __syncthreads();
+    const float ox = s_org[0], oy = s_org[1], oz = s_org[2], sx = s_scale[0], sy = s_scale[1], sz = s_scale[2];
+    auto cell_of = [&](float x, float y, float z) -> int {
+      const int ix = min(31, max(0, static_cast<int>((x - ox) * sx)));
+      const int iy = min(31, max(0, static_cast<int>((y - oy) * sy)));
+      const int iz = min(7, max(0, static_cast<int>((z - oz) * sz)));
+      return static_cast<int>(((part1by1(ix) | (part1by1(iy) << 1)) << 3) | static_cast<uint32_t>(iz));
+    };
+    for (int k = tid; k < n; k += FB_THREADS)
+      atomicAdd(&hist[cell_of(__ldg(xyz + 3 * k), __ldg(xyz + 3 * k + 1), __ldg(xyz + 3 * k + 2))], 1);
+    __syncthreads();
+    // exclusive scan of the 8192 counts: 8 per thread
+    int v[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = hist[tid * 8 + i]; sum += v[i]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    __shared__ int wtot[FB_WARPS];
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = wtot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      wtot[lane] = w;
+    }
+    __syncthreads();
+    int run = incl - sum + (warp ? wtot[warp - 1] : 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { cursor[tid * 8 + i] = run; run += v[i]; }
+    __syncthreads();
+    for (int k = tid; k < n; k += FB_THREADS) {
+      const float x = __ldg(xyz + 3 * k), y = __ldg(xyz + 3 * k + 1), z = __ldg(xyz + 3 * k + 2);
+      const int pos = atomicAdd(&cursor[cell_of(x, y, z)], 1);
+      sorted[pos] = make_float4(x, y, z, __int_as_float(k));
+    }
+    for (int k = n + tid; k < npad; k += FB_THREADS) sorted[k] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    __syncthreads();  // the CTA's own global writes are visible to all its threads from here on
+  }
+
+  // one bucket (64 points, two per lane): apply the centres in `mask`, refresh temps and the record
+  auto process_bucket = [&](int b, uint32_t mask, bool init, const float4& p0, const float4& p1) {
+    const int k0 = b * FB_BK + lane, k1 = k0 + 32;
+    const int o0 = __float_as_int(p0.w), o1 = __float_as_int(p1.w);
+    float t0, t1;
+    if (init) {
+      // sampling_gpu.cu:105-106: `if (mag <= 1e-3) continue;` -- a double comparison
+      const float m0 = __fmaf_rn(p0.z, p0.z, __fmaf_rn(p0.x, p0.x, __fmul_rn(p0.y, p0.y)));
+      const float m1 = __fmaf_rn(p1.z, p1.z, __fmaf_rn(p1.x, p1.x, __fmul_rn(p1.y, p1.y)));
+      t0 = (o0 >= 0 && !(static_cast<double>(m0) <= 1e-3)) ? 1e10f : -1.f;
+      t1 = (o1 >= 0 && !(static_cast<double>(m1) <= 1e-3)) ? 1e10f : -1.f;
+    } else {
+      t0 = temps[k0]; t1 = temps[k1];
+    }
+    while (mask) {
+      const int c = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float4 o = ctr[c];
+      t0 = fminf(sqdist3(p0.x - o.x, p0.y - o.y, p0.z - o.z), t0);
+      t1 = fminf(sqdist3(p1.x - o.x, p1.y - o.y, p1.z - o.z), t1);
+    }
+    temps[k0] = t0; temps[k1] = t1;
+    // lane-local best of the two points (value, then smaller key), the other one is the lane's rest
+    const uint32_t u0 = static_cast<uint32_t>(o0), u1 = static_cast<uint32_t>(o1);
+    const uint32_t key0 = o0 >= 0 ? ((log2bs ? __brev(u0 & bsmask) : 0u) | (u0 >> log2bs)) : 0xffffffffu;
+    const uint32_t key1 = o1 >= 0 ? ((log2bs ? __brev(u1 & bsmask) : 0u) | (u1 >> log2bs)) : 0xffffffffu;
+    const int v0 = __float_as_int(t0), v1 = __float_as_int(t1);  // t >= 0 or exactly -1: int order ok
+    const bool first1 = v1 > v0 || (v1 == v0 && key1 < key0);
+    const int vb = first1 ? v1 : v0, vrest = first1 ? v0 : v1;
+    const uint32_t key = first1 ? key1 : key0;
+    const float bx = first1 ? p1.x : p0.x, by = first1 ? p1.y : p0.y, bz = first1 ? p1.z : p0.z;
+    const float rx = first1 ? p0.x : p1.x, ry = first1 ? p0.y : p1.y, rz = first1 ? p0.z : p1.z;
+    const int vmax = __reduce_max_sync(0xffffffffu, vb);
+    const uint32_t kk = (vb == vmax) ? key : 0xffffffffu;
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, kk);
+    const bool win = (kk == kmin) && (vb == vmax);
+    const int first = __ffs(__ballot_sync(0xffffffffu, win)) - 1;  // unique unless the bucket is empty
+    // `second` = best value among the points the bucket does NOT report.  Exact coordinate duplicates
+    // of the winner are left out: they share its temp history, have larger keys (the winner is the
+    // smallest key among equals) and drop to exactly 0 the moment the winner is accepted, so they can
+    // never be the reference's next pick ahead of a candidate.  Morton order puts duplicates (dataset
+    // sampling with replacement, lib/joint/dataset.py:609-612) next to each other, so without this
+    // every duplicated point would cap the accepted batch at one sample.
+    const float wx = __shfl_sync(0xffffffffu, bx, first), wy = __shfl_sync(0xffffffffu, by, first),
+                wz = __shfl_sync(0xffffffffu, bz, first);
+    const int none = __float_as_int(-1.f);
+    const bool twin_b = (vb == vmax) && (bx == wx) && (by == wy) && (bz == wz);     // incl. the winner
+    const bool twin_r = (vrest == vmax) && (rx == wx) && (ry == wy) && (rz == wz);
+    const int sec = __reduce_max_sync(0xffffffffu, max(twin_b ? none : vb, twin_r ? none : vrest));
+    if (lane == first) {
+      bb_a[b] = make_float4(__int_as_float(vmax), __uint_as_float(kmin), bx, by);
+      bb_b[b] = make_float2(bz, __int_as_float(sec));
+    }
+  };
+
+  // ================= init: temps, bucket records, bucket and group boxes ==========================
+  for (int b = warp; b < nb; b += FB_WARPS)
+    process_bucket(b, 0u, true, sorted[b * FB_BK + lane], sorted[b * FB_BK + 32 + lane]);
+  // thread = bucket (tid < nb), warp = group of 32 consecutive buckets
+  Box bbox = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  if (tid < nb) {
+    for (int i = 0; i < FB_BK; ++i) {
+      const float4 p = sorted[tid * FB_BK + i];
+      if (__float_as_int(p.w) >= 0) {
+        bbox.lx = fminf(bbox.lx, p.x); bbox.ly = fminf(bbox.ly, p.y); bbox.lz = fminf(bbox.lz, p.z);
+        bbox.hx = fmaxf(bbox.hx, p.x); bbox.hy = fmaxf(bbox.hy, p.y); bbox.hz = fmaxf(bbox.hz, p.z);
+      }
+    }
+  }
+  Box gbox = bbox;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    gbox.lx = fminf(gbox.lx, __shfl_xor_sync(0xffffffffu, gbox.lx, o)); gbox.ly = fminf(gbox.ly, __shfl_xor_sync(0xffffffffu, gbox.ly, o));
+    gbox.lz = fminf(gbox.lz, __shfl_xor_sync(0xffffffffu, gbox.lz, o)); gbox.hx = fmaxf(gbox.hx, __shfl_xor_sync(0xffffffffu, gbox.hx, o));
+    gbox.hy = fmaxf(gbox.hy, __shfl_xor_sync(0xffffffffu, gbox.hy, o)); gbox.hz = fmaxf(gbox.hz, __shfl_xor_sync(0xffffffffu, gbox.hz, o));
+  }
+  if (tid == 0) {
+    ctr[0] = make_float4(x0, y0, z0, 0.f);  // sample 0 is index 0 (sampling_gpu.cu:89-90)
+    ctr_count = 1;
+    nwork = 0;
+    idxs[0] = 0;
+    if (oxyz) { oxyz[0] = x0; oxyz[1] = y0; oxyz[2] = z0; }
+  }
+  __syncthreads();
+  float bmax = tid < nb ? bb_a[tid].x : -1.f;
+  float gmax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(bmax)));
+  const bool has_group = warp * 32 < nb;  // warp-uniform
+
+#ifdef PN2_FB_DEBUG
+  long long dbg_items = 0, dbg_t[5] = {0, 0, 0, 0, 0}, dbg_prev = clock64();
+  printf(tid == 0 ? "fps_bucket[%d]: prologue+init %lld cycles\n" : "", scene, dbg_prev - dbg_t0);
+  int dbg_rounds = 0;
+#define FB_T(i) { const long long _t = clock64(); dbg_t[i] += _t - dbg_prev; dbg_prev = _t; }
+#else
+#define FB_T(i)
+#endif
+  int j = 1;
+  while (j < m) {
+    // ---------------- 1. prune: which (bucket, centre) pairs can change anything ------------------
+    const int K = ctr_count;
+    if (has_group && gmax >= 0.f) {
+      float4 myc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < K) myc = ctr[lane];
+      const bool gaff = lane < K && !(box_d2(gbox, myc.x, myc.y, myc.z) * 0.9999f >= gmax);
+      uint32_t gmask = __ballot_sync(0xffffffffu, gaff);
+      if (gmask != 0u) {
+        uint32_t mask = 0u;
+        const bool live = tid < nb && bmax >= 0.f;
+        while (gmask) {
+          const int c = __ffs(gmask) - 1;
+          gmask &= gmask - 1;
+          const float4 o = ctr[c];
+          if (live && !(box_d2(bbox, o.x, o.y, o.z) * 0.9999f >= bmax)) mask |= 1u << c;
+        }
+        const uint32_t any = __ballot_sync(0xffffffffu, mask != 0u);
+        if (any) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&nwork, __popc(any));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (mask) work[base + __popc(any & lt)] = static_cast<uint32_t>(tid) | (mask << 16);
+        }
+      }
+    }
+    __syncthreads();
+    FB_T(0)
+    // ---------------- 2. update the surviving buckets (next item's points are fetched while the
+    // current one is processed: the L2 latency of the sorted array is off the critical path) --------
+    const int nw = nwork;
+    {
+      uint32_t item = 0u;
+      float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+      if (warp < nw) {
+        item = work[warp];
+        const float4* src = sorted + (item & 0xffffu) * FB_BK + lane;
+        p0 = src[0]; p1 = src[32];
+      }
+      for (int i = warp; i < nw; i += FB_WARPS) {
+        const uint32_t cur = item;
+        const float4 c0 = p0, c1 = p1;
+        if (i + FB_WARPS < nw) {
+          item = work[i + FB_WARPS];
+          const float4* src = sorted + (item & 0xffffu) * FB_BK + lane;
+          p0 = src[0]; p1 = src[32];
+        }
+        process_bucket(static_cast<int>(cur & 0xffffu), cur >> 16, false, c0, c1);
+      }
+    }
+    __syncthreads();
+    FB_T(1)
+#ifdef PN2_FB_DEBUG
+    dbg_items += nw; ++dbg_rounds;
+#endif
+    // ---------------- 3. select: thread = bucket, warp = group ---------------------------------------
+    {
+      int best = __float_as_int(-1.f), second = __float_as_int(-1.f);
+      uint32_t bkey = 0xffffffffu;
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      float rz = 0.f;
+      if (tid < nb) {
+        r = bb_a[tid];
+        const float2 q = bb_b[tid];
+        best = __float_as_int(r.x); bkey = __float_as_uint(r.y);
+        second = __float_as_int(q.y); rz = q.x;
+      }
+      bmax = __int_as_float(best);
+      const int vmax = __reduce_max_sync(0xffffffffu, best);
+      gmax = __int_as_float(vmax);
+      const uint32_t kk = (best == vmax) ? bkey : 0xffffffffu;
+      const uint32_t kmin = __reduce_min_sync(0xffffffffu, kk);
+      const bool win = (kk == kmin) && (best == vmax);
+      const int first = __ffs(__ballot_sync(0xffffffffu, win)) - 1;
+      const float wx = __shfl_sync(0xffffffffu, r.z, first), wy = __shfl_sync(0xffffffffu, r.w, first),
+                  wz = __shfl_sync(0xffffffffu, rz, first);
+      // a neighbouring bucket whose best is an exact coordinate twin of the warp's winner (duplicates
+      // split by a bucket boundary) contributes its `second`, not its best -- same argument as above
+      const bool twin = (best == vmax) && (r.z == wx) && (r.w == wy) && (rz == wz);
+      const int wsec = __reduce_max_sync(0xffffffffu, (lane == first || twin) ? second : best);
+      if (lane == first) {
+        w_vk[warp] = make_uint2(static_cast<uint32_t>(vmax), kmin);
+        w_xyz[warp] = make_float4(r.z, r.w, rz, __int_as_float(wsec));
+      }
+      if (tid == 0) nwork = 0;
+    }
+    __syncthreads();
+    FB_T(2)
+    // ---------------- 4. accept: greedy FPS on the 32 warp candidates (exact) ------------------------
+    if (warp == 0) {
+      const uint2 r = w_vk[lane];
+      const float4 w = w_xyz[lane];
+      int cv = static_cast<int>(r.x);
+      const uint32_t ck = r.y;
+      const float cx = w.x, cy = w.y, cz = w.z;
+      const int bnd = max(__reduce_max_sync(0xffffffffu, __float_as_int(w.w)), 0);
+      const int room = min(FB_KMAX, m - j);
+      int k = 0;
+      int rv = __reduce_max_sync(0xffffffffu, cv);
+      if (rv < 0) {
+        // no eligible point anywhere: every reference thread reports besti = 0 (key of index 0 is 0)
+        if (lane == 0) ctr[0] = make_float4(x0, y0, z0, __uint_as_float(0u));
+        k = 1;
+      } else {
+        for (;;) {
+          uint32_t tie = __ballot_sync(0xffffffffu, cv == rv);
+          if (tie & (tie - 1)) {  // equal values: the smallest key wins (keys are unique)
+            const uint32_t kk = (cv == rv) ? ck : 0xffffffffu;
+            const uint32_t kmin = __reduce_min_sync(0xffffffffu, kk);
+            tie = __ballot_sync(0xffffffffu, kk == kmin);
+          }
+          const int src = __ffs(tie) - 1;
+          const float ax = __shfl_sync(0xffffffffu, cx, src), ay = __shfl_sync(0xffffffffu, cy, src),
+                      az = __shfl_sync(0xffffffffu, cz, src);
+          const uint32_t ak = __shfl_sync(0xffffffffu, ck, src);
+          if (lane == 0) ctr[k] = make_float4(ax, ay, az, __uint_as_float(ak));
+          if (++k >= room) break;
+          cv = __float_as_int(fminf(sqdist3(cx - ax, cy - ay, cz - az), __int_as_float(cv)));
+          rv = __reduce_max_sync(0xffffffffu, cv);
+          if (!(rv > bnd)) break;
+        }
+      }
+      __syncwarp();
+      if (lane < k) {
+        const float4 cc = ctr[lane];
+        const uint32_t mykey = __float_as_uint(cc.w);
+        const uint32_t row = mykey & rowmask;
+        const uint32_t vv = log2bs ? __brev(mykey & ~rowmask) : 0u;
+        idxs[j + lane] = static_cast<int>(vv + (row << log2bs));
+        if (oxyz) { oxyz[3 * (j + lane)] = cc.x; oxyz[3 * (j + lane) + 1] = cc.y; oxyz[3 * (j + lane) + 2] = cc.z; }
+      }
+      if (lane == 0) ctr_count = k;
+    }
+    __syncthreads();
+    FB_T(3)
+    j += ctr_count;
+  }
+#ifdef PN2_FB_DEBUG
+  if (tid == 0)
+    printf("fps_bucket[%d]: total %lld cycles; rounds", scene, clock64() - dbg_t0);
+  if (tid == 0)
+    printf(" rounds %d items %lld (%.1f/round) cycles/round: prune %lld update %lld select %lld accept %lld\n", dbg_rounds,
+           dbg_items, double(dbg_items) / dbg_rounds, dbg_t[0] / dbg_rounds, dbg_t[1] / dbg_rounds, dbg_t[2] / dbg_rounds,
+           dbg_t[3] / dbg_rounds);
+#endif
+}
+
+}  // namespace
+
+// Largest scene the single-CTA kernel holds on chip: 4 B/point of running minima + 28 B per 64-point bucket
+// within the 227 KB of shared memory of an sm_100a CTA.
+bool fps_bucket_supported(int n) { return n >= 16384 && n <= 50176; }
+
+int fps_bucket_run(int b, int n, int m, int log2bs, const float* dataset, int* idxs, float* new_xyz,
+                   cudaStream_t stream) {
+  FbArgs a;
+  a.xyz = dataset; a.idxs = idxs; a.new_xyz = new_xyz;
+  a.n = n; a.m = m; a.log2bs = log2bs;
+  a.nb = (n + FB_BK - 1) / FB_BK;
+  a.npad = a.nb * FB_BK;
+  PN2_REQUIRE(a.nb <= FB_THREADS, "fps_bucket: too many buckets");
+  const size_t smem = static_cast<size_t>(a.npad) * 4 + static_cast<size_t>(a.nb) * (16 + 8 + 4) + 64;
+  PN2_REQUIRE(smem <= 227 * 1024 && static_cast<size_t>(a.npad) * 4 >= 2 * FB_CELLS * sizeof(int),
+              "fps_bucket: n=%d outside the supported range", n);
+  float4* sorted = nullptr;
+  PN2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sorted), static_cast<size_t>(b) * a.npad * sizeof(float4), stream));
+  a.sorted = sorted;
+  cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e == cudaSuccess) {
+    fps_bucket_kernel<<<b, FB_THREADS, smem, stream>>>(a);
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(sorted, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "fps_bucket_kernel");
+  return PN2_OK;
+}
+
+}  // namespace pn2

@@ -39,6 +39,13 @@ FPS_CASES = {
     "cluster_20000": (lambda: cloud(18, 1, 20000)[..., :3].contiguous(), 512),
     "cluster_lattice_13824": (lambda: _lattice(24), 600),
     "cluster_all_origin": (lambda: (cloud(19, 1, 10000)[..., :3] * 0.004).contiguous(), 32),
+    # 16384 <= n <= 45056: single-CTA bucketed kernel with spatial pruning (fps_bucket.cu)
+    "bucket_lattice_27000": (lambda: _lattice(30), 900),
+    "bucket_dups_30000": (lambda: cloud(23, 2, 30000, dup_frac=0.5, origin_pts=7)[..., :3].contiguous(), 700),
+    "bucket_all_origin_20000": (lambda: (cloud(24, 1, 20000)[..., :3] * 0.004).contiguous(), 40),
+    "bucket_identical_17000": (lambda: torch.ones(1, 17000, 3) * 0.7, 50),
+    "bucket_45056_to_n": (lambda: cloud(25, 1, 45056, extent=3.0)[..., :3].contiguous(), 1500),
+    "bucket_16384_m_all": (lambda: cloud(26, 1, 16384, extent=0.5)[..., :3].contiguous(), 3000),
 }
 
 
@@ -56,9 +63,10 @@ def test_fps_bit_exact(pkg, oracle, cuda, name):
     assert torch.equal(new_xyz.cpu(), ref_xyz)
 
 
-def test_fps_nan_inf_coordinates(pkg, oracle, cuda):
-    x = cloud(10, 1, 900)[..., :3].contiguous()
-    x[0, 17, 1] = float("nan"); x[0, 400] = float("inf")
+@pytest.mark.parametrize("n", [900, 9000, 20000])
+def test_fps_nan_inf_coordinates(pkg, oracle, cuda, n):
+    x = cloud(10, 1, n)[..., :3].contiguous()
+    x[0, 17, 1] = float("nan"); x[0, 400] = float("inf"); x[0, 555, 2] = float("-inf")
     want = oracle.ext.furthest_point_sampling(x, 40)
     got = pkg._ext.furthest_point_sampling(x.to(cuda), 40)
     assert torch.equal(got.cpu(), want)
