@@ -77,6 +77,18 @@ def _call(L, fn, name, args, device):
         raise Pn2Error("%s failed (status %d): %s" % (name, rc, L.pn2_last_error().decode()))
 
 
+def set_option(name, value):
+    """pn2_set_option: "fps_bucket" (0 = low-latency cluster FPS, 1 = single-SM bucketed FPS for
+    throughput with several batches in flight), "bq_grid" (hashed-grid ball query on/off)."""
+    L = lib()
+    if L.pn2_set_option(name.encode(), int(value)) != 0:
+        raise Pn2Error(L.pn2_last_error().decode())
+
+
+def get_option(name):
+    return int(lib().pn2_get_option(name.encode()))
+
+
 # ---- argument checks with the reference's messages (include/utils.h:10-30) -----------------------
 
 def check_contiguous(t, name):

@@ -1,4 +1,5 @@
 // Library identity and error plumbing for lib3dvlp_b200.so (see include/pointnet2_b200.h).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -47,7 +48,41 @@ int* device_err_flag() {
   return g_err_flag[dev];
 }
 
+// ---- run-time options ----------------------------------------------------------------------------
+static const char* const kOptName[OPT_COUNT] = {"fps_bucket", "bq_grid"};
+static const char* const kOptEnv[OPT_COUNT] = {"PN2_FPS_BUCKET", "PN2_BQ_GRID"};
+static const int kOptDefault[OPT_COUNT] = {0, 1};
+static int g_opt[OPT_COUNT] = {-1, -1};
+
+int option_value(Option o) {
+  int v = __atomic_load_n(&g_opt[o], __ATOMIC_RELAXED);
+  if (v < 0) {
+    const char* e = getenv(kOptEnv[o]);
+    v = e ? atoi(e) : kOptDefault[o];
+    if (v < 0) v = 0;
+    __atomic_store_n(&g_opt[o], v, __ATOMIC_RELAXED);
+  }
+  return v;
+}
+
 }  // namespace pn2
+
+extern "C" int pn2_set_option(const char* name, int value) {
+  for (int i = 0; i < pn2::OPT_COUNT; ++i) {
+    if (name && strcmp(name, pn2::kOptName[i]) == 0) {
+      __atomic_store_n(&pn2::g_opt[i], value < 0 ? 0 : value, __ATOMIC_RELAXED);
+      return PN2_OK;
+    }
+  }
+  pn2::set_error("set_option: unknown option '%s' (known: fps_bucket, bq_grid)", name ? name : "(null)");
+  return PN2_ERR_INVALID;
+}
+
+extern "C" int pn2_get_option(const char* name) {
+  for (int i = 0; i < pn2::OPT_COUNT; ++i)
+    if (name && strcmp(name, pn2::kOptName[i]) == 0) return pn2::option_value(static_cast<pn2::Option>(i));
+  return -1;
+}
 
 extern "C" int pn2_poll_device_error(int* flag_out, void* stream) {
   int* p = pn2::device_err_flag();

@@ -50,6 +50,10 @@ inline int opt_n_threads(int work_size) {
 
 int sm_count();
 
+// run-time options (pn2_set_option); initial values come from the environment
+enum Option { OPT_FPS_BUCKET = 0, OPT_BQ_GRID = 1, OPT_COUNT = 2 };
+int option_value(Option o);
+
 // ---- device helpers -------------------------------------------------------------------------
 
 // Squared distance exactly as nvcc contracts the reference expression

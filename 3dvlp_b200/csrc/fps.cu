@@ -439,9 +439,13 @@ int fps_run(int b, int n, int m, const float* dataset, int* idxs, float* new_xyz
 #endif
   PN2_REQUIRE(a.err != nullptr, "furthest_point_sampling: cannot allocate the device error flag");
 
-  // mid-size scenes (SA1 at 40k points): single-CTA bucketed kernel with spatial pruning
-  static const int use_bucket = env_int("PN2_FPS_BUCKET", 1);
-  if (use_bucket && fps_bucket_supported(n)) return fps_bucket_run(b, n, m, log2bs, dataset, idxs, new_xyz, stream);
+  // Two algorithms for large scenes (both bit-exact):
+  //   cluster kernel (default)  16 SMs per scene, lowest latency for a single batch;
+  //   bucketed kernel           1 SM per scene with spatial pruning: ~2x the latency but 1/16 of the
+  //                             SM footprint, the right choice when several batches are in flight.
+  // Selected with pn2_set_option("fps_bucket", 0|1) (initial value: env PN2_FPS_BUCKET, default 0).
+  if (option_value(OPT_FPS_BUCKET) && fps_bucket_supported(n))
+    return fps_bucket_run(b, n, m, log2bs, dataset, idxs, new_xyz, stream);
 
   static const int force_cluster = env_int("PN2_FPS_CLUSTER", 0);
   static const int force_threads = env_int("PN2_FPS_THREADS", 0);

@@ -50,34 +50,44 @@ struct SaArgs {
   long long total_rows;  // B * npoint * ns
 };
 
-template <int CPL, int CD>  // channels per lane in layer 1 (C1 = 32 * CPL), raw feature channels
-__global__ void __launch_bounds__(SA_THREADS) sa_fused_kernel(const SaArgs a) {
+// NG = independent 128-thread groups per CTA.  Each group runs the tile loop on its own activation tile,
+// TMEM columns and mbarrier; the folded weights in shared memory are shared.  When the weights leave room
+// for only one CTA per SM (SA2-SA4: 96 KB) two groups give the SM a second tile to work on while the
+// first waits for its gather / MMA / TMEM round trips.
+template <int CPL, int CD, int NG>  // channels per lane in layer 1 (C1 = 32 * CPL), raw feature channels
+__global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_mma;
+  __shared__ __align__(8) uint64_t bar_w, bar_mma_g[NG];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_b2[128], s_b3[256];
 
   constexpr int C1 = 32 * CPL;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = threadIdx.x / SA_THREADS;            // group of this thread
+  const int tid = threadIdx.x % SA_THREADS, lane = tid & 31, warp = tid >> 5;  // within the group
   const int C2 = a.C2, C3 = a.C3, ns = a.ns;
+  uint64_t& bar_mma = bar_mma_g[grp];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w2_bytes = static_cast<uint32_t>(C2) * C1 * 2, w3_bytes = static_cast<uint32_t>(C3) * C2 * 2;
-  const uint32_t s_w2 = base, s_w3 = base + w2_bytes, s_x = base + w2_bytes + w3_bytes;  // all 1 KB multiples
-  const uint32_t tmem_cols = (C3 > 128 || C2 > 128) ? 256u : 128u;
+  const uint32_t x_bytes = 128u * static_cast<uint32_t>(C1 > C2 ? C1 : C2) * 2u;
+  const uint32_t s_w2 = base, s_w3 = base + w2_bytes, s_x = base + w2_bytes + w3_bytes + grp * x_bytes;  // 1 KB multiples
+  const uint32_t group_cols = (C3 > 128 || C2 > 128) ? 256u : 128u;
+  const uint32_t tmem_cols = group_cols * NG;
 
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_mma, 1);
+    for (int g = 0; g < NG; ++g) mbar_init(&bar_mma_g[g], 1);
     fence_mbar_init_cluster();
   }
-  for (int i = tid; i < C2; i += SA_THREADS) s_b2[i] = a.b2[i];
-  for (int i = tid; i < C3; i += SA_THREADS) s_b3[i] = a.b3[i];
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, tmem_cols);
+  for (int i = threadIdx.x; i < C2; i += SA_THREADS * NG) s_b2[i] = a.b2[i];
+  for (int i = threadIdx.x; i < C3; i += SA_THREADS * NG) s_b3[i] = a.b3[i];
+  if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot, tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem_d = tmem_slot;
-  if (tid == 0) {
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_d = tmem_base + grp * group_cols;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(SA_THREADS) : "memory"); };
+  if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(&bar_w, w2_bytes + w3_bytes);
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     tc::bulk_g2s(gen, a.w2p, w2_bytes, &bar_w);
@@ -101,7 +111,8 @@ __global__ void __launch_bounds__(SA_THREADS) sa_fused_kernel(const SaArgs a) {
   uint32_t phase = 0;
   bool weights_ready = false, failed = false;
 
-  for (long long tile = blockIdx.x; tile < n_tiles && !failed; tile += gridDim.x) {
+  for (long long tile = static_cast<long long>(blockIdx.x) * NG + grp; tile < n_tiles && !failed;
+       tile += static_cast<long long>(gridDim.x) * NG) {
     const long long r0 = tile * 128;
     // ---------------- layer 1: build X1 (bf16) for rows warp*32 .. warp*32+31 -------------------
     {
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(SA_THREADS) sa_fused_kernel(const SaArgs a) {
     }
     fence_proxy_async_smem();
     tc::fence_before_sync();
-    __syncthreads();
+    group_sync();
     if (!weights_ready) {
       if (!mbar_wait(&bar_w, 0)) { failed = true; break; }
       weights_ready = true;
@@ -211,7 +222,7 @@ __global__ void __launch_bounds__(SA_THREADS) sa_fused_kernel(const SaArgs a) {
     }
     fence_proxy_async_smem();
     tc::fence_before_sync();
-    __syncthreads();
+    group_sync();
     // ---------------- layer 3 (transposed): D3[h] = W3[h*128 .. +128] . X2^T -------------------
     if (tid == 0) {
       tc::fence_after_sync();
@@ -258,16 +269,16 @@ __global__ void __launch_bounds__(SA_THREADS) sa_fused_kernel(const SaArgs a) {
   if (failed && tid == 0) atomicExch(a.err, 2);
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
+  if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, tmem_cols);
 }
 
-template <int CPL>
+template <int CPL, int NG>
 int launch_cd(int cd, const SaArgs& a, int grid, size_t smem, cudaStream_t s) {
 #define PN2_SA_CASE(CDV)                                                                                   \
   case CDV: {                                                                                              \
-    PN2_CUDA(cudaFuncSetAttribute(sa_fused_kernel<CPL, CDV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+    PN2_CUDA(cudaFuncSetAttribute(sa_fused_kernel<CPL, CDV, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                   static_cast<int>(smem)));                                                \
-    sa_fused_kernel<CPL, CDV><<<grid, SA_THREADS, smem, s>>>(a);                                           \
+    sa_fused_kernel<CPL, CDV, NG><<<grid, SA_THREADS * NG, smem, s>>>(a);                                  \
     break;                                                                                                 \
   }
   switch (cd) {
@@ -310,16 +321,24 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
   a.total_rows = static_cast<long long>(b) * npoint * nsample;
   a.err = device_err_flag();
   PN2_REQUIRE(a.err != nullptr, "sa_group_mlp: cannot allocate the device error flag");
-  const size_t smem = static_cast<size_t>(c2) * c1 * 2 + static_cast<size_t>(c3) * c2 * 2 +
-                      128 * static_cast<size_t>(c1 > c2 ? c1 : c2) * 2 + 1024;
+  const size_t w_bytes = static_cast<size_t>(c2) * c1 * 2 + static_cast<size_t>(c3) * c2 * 2;
+  const size_t x_bytes = 128 * static_cast<size_t>(c1 > c2 ? c1 : c2) * 2;
   const long long tiles = (a.total_rows + 127) / 128;
-  const int per_sm = smem <= 56 * 1024 ? 4 : (smem <= 113 * 1024 ? 2 : 1);
   const int tm_cols = (c3 > 128 || c2 > 128) ? 256 : 128;
-  const int per_sm_tm = 512 / tm_cols;
-  const int resident = per_sm < per_sm_tm ? per_sm : per_sm_tm;
+  // small weight sets: several independent 128-thread CTAs per SM; big ones: one CTA with two groups
+  const size_t smem1 = w_bytes + x_bytes + 1024;
+  const int per_sm1 = smem1 <= 56 * 1024 ? 4 : (smem1 <= 113 * 1024 ? 2 : 1);
+  const int ng = (per_sm1 == 1 && tm_cols * 2 <= 512 && w_bytes + 2 * x_bytes + 1024 <= 227 * 1024) ? 2 : 1;
+  const size_t smem = w_bytes + ng * x_bytes + 1024;
+  const int per_sm_tm = 512 / (tm_cols * ng);
+  const int resident = ng == 2 ? 1 : (per_sm1 < per_sm_tm ? per_sm1 : per_sm_tm);
   long long grid = static_cast<long long>(sm_count()) * resident;
-  if (grid > tiles) grid = tiles;
+  if (grid * ng > tiles) grid = (tiles + ng - 1) / ng;
   cudaStream_t s = as_stream(stream);
-  if (c1 == 128) return launch_cd<4>(c_direct, a, static_cast<int>(grid), smem, s);
-  return launch_cd<2>(c_direct, a, static_cast<int>(grid), smem, s);
+  if (ng == 2) {
+    if (c1 == 128) return launch_cd<4, 2>(c_direct, a, static_cast<int>(grid), smem, s);
+    return launch_cd<2, 2>(c_direct, a, static_cast<int>(grid), smem, s);
+  }
+  if (c1 == 128) return launch_cd<4, 1>(c_direct, a, static_cast<int>(grid), smem, s);
+  return launch_cd<2, 1>(c_direct, a, static_cast<int>(grid), smem, s);
 }

@@ -134,10 +134,9 @@ extern "C" int pn2_ball_query(int b, int n, int m, float radius, int nsample, co
   PN2_REQUIRE(n >= 0 && new_xyz && idx && (xyz || n == 0), "ball_query: bad arguments");
   PN2_REQUIRE(b <= 65535, "ball_query: batch %d exceeds the grid limit", b);
   const float radius2 = radius * radius;  // fp32 product, ball_query_gpu.cu:27
-  // large clouds: hashed-grid search (identical output, ~100x fewer distance tests); PN2_BQ_GRID=0
-  // forces the linear scan
-  static const bool use_grid = !(getenv("PN2_BQ_GRID") && atoi(getenv("PN2_BQ_GRID")) == 0);
-  if (use_grid && n >= 4096 && radius2 > 0.f && std::isfinite(radius) && fabsf(radius) > 1e-6f)
+  // large clouds: hashed-grid search (identical output, ~100x fewer distance tests);
+  // pn2_set_option("bq_grid", 0) / PN2_BQ_GRID=0 forces the linear scan
+  if (option_value(OPT_BQ_GRID) && n >= 4096 && radius2 > 0.f && std::isfinite(radius) && fabsf(radius) > 1e-6f)
     return ball_query_grid(b, n, m, radius, nsample, new_xyz, xyz, idx, as_stream(stream));
   const int per_cta = BQ_CPW * BQ_WARPS;
   dim3 grid((m + per_cta - 1) / per_cta, b);

@@ -18,32 +18,40 @@ class GraphedBackbone:
     next call.  Falls back to eager execution (``self.graph is None``) if capture is not possible.
     """
 
-    def __init__(self, backbone, example_batch, warmup=3):
+    def __init__(self, backbone, example_batch, warmup=3, throughput=False):
         if backbone.training:
             raise RuntimeError("GraphedBackbone needs the backbone in eval() mode")
         if not example_batch.is_cuda or example_batch.dtype != torch.float32:
             raise RuntimeError("CPU not supported")
         self.backbone = backbone
-        self.static_in = example_batch.clone().contiguous()
-        self.graph = None
-        self.static_out = None
-        self.capture_error = None
-        cur = torch.cuda.current_stream(self.static_in.device)
-        s = torch.cuda.Stream(device=self.static_in.device)
-        s.wait_stream(cur)
-        with torch.no_grad(), torch.cuda.stream(s):
-            for _ in range(max(1, warmup)):  # fills every host-side cache (plans, occupancy, pools)
-                backbone({"point_clouds": self.static_in})
-        cur.wait_stream(s)
-        torch.cuda.synchronize(self.static_in.device)
+        # throughput=True captures the single-SM bucketed FPS (meant for several graphs in flight on
+        # separate streams); the default captures the low-latency 16-SM cluster FPS
+        from . import _lib
+        prev = _lib.get_option("fps_bucket")
+        _lib.set_option("fps_bucket", 1 if throughput else 0)
         try:
-            g = torch.cuda.CUDAGraph()
-            with torch.no_grad(), torch.cuda.graph(g):
-                out = backbone({"point_clouds": self.static_in})
-            self.graph, self.static_out = g, out
-        except Exception as ex:  # pragma: no cover - depends on driver behaviour
-            self.capture_error = repr(ex)
+            self.static_in = example_batch.clone().contiguous()
+            self.graph = None
+            self.static_out = None
+            self.capture_error = None
+            cur = torch.cuda.current_stream(self.static_in.device)
+            s = torch.cuda.Stream(device=self.static_in.device)
+            s.wait_stream(cur)
+            with torch.no_grad(), torch.cuda.stream(s):
+                for _ in range(max(1, warmup)):  # fills every host-side cache (plans, occupancy, pools)
+                    backbone({"point_clouds": self.static_in})
+            cur.wait_stream(s)
             torch.cuda.synchronize(self.static_in.device)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(g):
+                    out = backbone({"point_clouds": self.static_in})
+                self.graph, self.static_out = g, out
+            except Exception as ex:  # pragma: no cover - depends on driver behaviour
+                self.capture_error = repr(ex)
+                torch.cuda.synchronize(self.static_in.device)
+        finally:
+            _lib.set_option("fps_bucket", prev)
 
     def __call__(self, point_clouds):
         self.static_in.copy_(point_clouds, non_blocking=True)

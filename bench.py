@@ -239,11 +239,11 @@ def per_op_profile(torch, L, model, batch, reps=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=24)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=4, help="batches in flight (graph replays on separate streams)")
+    ap.add_argument("--depth", type=int, default=12, help="batches in flight (graph replays on separate streams)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -292,7 +292,8 @@ def main():
     # `depth` batches in flight: FPS is a latency-bound serial chain that leaves most SMs idle, so two
     # graph replays on two streams overlap one batch's sampling chain with the other's feature path.
     depth = max(1, args.depth)
-    graphs = [pkg.GraphedBackbone(model, dev_pool[0]) for _ in range(depth)]
+    throughput_mode = depth >= 6  # many batches in flight: 1-SM bucketed FPS; few: 16-SM cluster FPS
+    graphs = [pkg.GraphedBackbone(model, dev_pool[0], throughput=throughput_mode) for _ in range(depth)]
     lanes = [torch.cuda.Stream(device=dev) for _ in range(depth)]
     graphed = graphs[0]
     execution = "cuda_graph" if graphed.graph is not None else "eager (graph capture failed: %s)" % graphed.capture_error
@@ -400,7 +401,8 @@ def main():
                     "c_in": C_IN, "l2": "rotating pool of %d input batches (%.0f MB > L2)" % (
                         POOL, POOL * SCENES_PER_GPU * N_POINTS * 4 * (3 + C_IN) / 1e6),
                     "parallelism": "scene-sharded dp%d, no data-path collective" % world,
-                    "execution": execution, "batches_in_flight": depth},
+                    "execution": execution, "batches_in_flight": depth,
+                    "fps_algorithm": "bucketed single-SM (throughput mode)" if throughput_mode else "16-CTA cluster (latency mode)"},
                 "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_ops": roofline_ops[:24]}

@@ -37,6 +37,14 @@ int pn2_device_arch(int* major, int* minor); /* compute capability of the curren
 /* Synchronises `stream` and reads (then clears) the device-side protocol error flag: 0 = none,
  * 1 = FPS cluster exchange timed out, 2 = tensor-core pipeline timed out.  Debug aid. */
 int pn2_poll_device_error(int* flag_out, void* stream);
+/* Run-time options (process-wide; initial value from the environment variable in brackets):
+ *   "fps_bucket" [PN2_FPS_BUCKET, default 0]  1 = large scenes (16 384..50 176 points) use the single-SM
+ *                bucketed FPS kernel with spatial pruning instead of the 16-SM cluster kernel: same
+ *                output, ~2x the latency of one batch, 1/16 of the SM footprint (throughput mode);
+ *   "bq_grid"    [PN2_BQ_GRID, default 1]     0 = ball query always uses the linear scan.
+ * pn2_get_option returns the value, or -1 for an unknown name. */
+int pn2_set_option(const char* name, int value);
+int pn2_get_option(const char* name);
 
 /* ---------------------------------------------------------------------------------------------
  * The nine launchers of pointnet2._ext
