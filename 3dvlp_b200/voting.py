@@ -1,0 +1,127 @@
+"""Hough voting front end: VotingModule + vote L2-normalisation + vote aggregation.
+
+Drop-in for /root/reference/models/base_module/voting_module.py:10-59 (``VotingModule``: same
+constructor, parameter names conv1/conv2/conv3/bn1/bn2, forward signature and outputs) and a
+``VoteNetFrontEnd`` that mirrors the detection branch of JointNet.forward up to the aggregated votes
+(models/jointnet/jointnet.py:138-154 + models/proposal_module/proposal_module_fcos.py:36-43,76-85) with
+the reference's attribute names (``backbone_net``, ``vgen``, ``proposal.vote_aggregation``) so a 3DVLP
+checkpoint's entries for these parts load unchanged.  SURVEY.md section 8(f) rank 1 ("next" row).
+
+Eval fast path: the three 1x1 Conv1d layers run on the tcgen05 linear kernel (BatchNorm folded,
+bf16 operands / fp32 accumulate, hidden activations bf16): 4 launches + 2 elementwise adds.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import tensorcore as tcm
+from .backbone import Pointnet2Backbone
+from .pointnet2_modules import PointnetSAModuleVotes
+
+
+def _fold_conv_bn(conv, bn):
+    w = conv.weight.detach().float().reshape(conv.weight.shape[0], -1)
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    if bn is not None:
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * scale[:, None]
+        b = (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    return w.contiguous(), b.contiguous()
+
+
+class VotingModule(nn.Module):
+    def __init__(self, vote_factor, seed_feature_dim):
+        """vote_factor votes per seed; vote features keep seed_feature_dim channels (residual)."""
+        super().__init__()
+        self.vote_factor = vote_factor
+        self.in_dim = seed_feature_dim
+        self.out_dim = self.in_dim
+        self.conv1 = torch.nn.Conv1d(self.in_dim, self.in_dim, 1)
+        self.conv2 = torch.nn.Conv1d(self.in_dim, self.in_dim, 1)
+        self.conv3 = torch.nn.Conv1d(self.in_dim, (3 + self.out_dim) * self.vote_factor, 1)
+        self.bn1 = torch.nn.BatchNorm1d(self.in_dim)
+        self.bn2 = torch.nn.BatchNorm1d(self.in_dim)
+        self._fused = None
+
+    def _plan(self):
+        key = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        if self._fused is not None and self._fused["key"] == key:
+            return self._fused
+        w1, b1 = _fold_conv_bn(self.conv1, self.bn1)
+        w2, b2 = _fold_conv_bn(self.conv2, self.bn2)
+        w3, b3 = _fold_conv_bn(self.conv3, None)
+        w_off = torch.zeros(16, w3.shape[1], device=w3.device)  # 3 offset rows padded to N = 16
+        w_off[:3] = w3[:3]
+        b_off = torch.zeros(16, device=w3.device)
+        b_off[:3] = b3[:3]
+        self._fused = {"key": key, "l1": (tcm.PackedWeight(w1), b1), "l2": (tcm.PackedWeight(w2), b2),
+                       "off": (tcm.PackedWeight(w_off), b_off),
+                       "res": (tcm.PackedWeight(w3[3:].contiguous()), b3[3:].contiguous())}
+        return self._fused
+
+    def forward(self, seed_xyz, seed_features):
+        """seed_xyz (B, num_seed, 3), seed_features (B, C, num_seed) ->
+        vote_xyz (B, num_seed*vote_factor, 3), vote_features (B, C, num_seed*vote_factor)."""
+        batch_size, num_seed = seed_xyz.shape[0], seed_xyz.shape[1]
+        num_vote = num_seed * self.vote_factor
+        if (not self.training and not torch.is_grad_enabled() and seed_xyz.is_cuda and self.vote_factor == 1
+                and self.in_dim % 64 == 0 and self.in_dim <= 256):
+            p = self._plan()
+            rows = getattr(seed_features, "_pn2_rows", None)
+            if rows is None or rows.shape != (batch_size * num_seed, self.in_dim):
+                rows = tcm.pack_rows(seed_features.contiguous().float(), self.in_dim)
+            h = tcm.linear(rows, p["l1"][0], p["l1"][1], relu=True, out="bf16")
+            h = tcm.linear(h, p["l2"][0], p["l2"][1], relu=True, out="bf16")
+            off = tcm.linear(h, p["off"][0], p["off"][1], relu=False, out="f32")           # (B*n, 16)
+            res = tcm.linear(h, p["res"][0], p["res"][1], relu=False, out="cm", rows_per_batch=num_seed)
+            vote_xyz = seed_xyz + off[:, :3].reshape(batch_size, num_seed, 3)
+            vote_features = seed_features + res
+            return vote_xyz.contiguous(), vote_features
+        # generic path: the reference arithmetic (voting_module.py:44-59)
+        net = F.relu(self.bn1(self.conv1(seed_features)))
+        net = F.relu(self.bn2(self.conv2(net)))
+        net = self.conv3(net)  # (B, (3+out_dim)*vote_factor, num_seed)
+        net = net.transpose(2, 1).view(batch_size, num_seed, self.vote_factor, 3 + self.out_dim).contiguous()
+        offset = net[:, :, :, 0:3]
+        vote_xyz = (seed_xyz.unsqueeze(2) + offset).contiguous().view(batch_size, num_vote, 3)
+        residual_features = net[:, :, :, 3:]
+        vote_features = seed_features.transpose(2, 1).unsqueeze(2).contiguous() + residual_features
+        vote_features = vote_features.contiguous().view(batch_size, num_vote, self.out_dim)
+        return vote_xyz, vote_features.transpose(2, 1).contiguous()
+
+
+class _VoteAggregation(nn.Module):
+    """Holder with the attribute name the reference's ProposalModule uses (proposal_module_fcos.py:36-43)."""
+
+    def __init__(self, num_proposal=256, seed_feat_dim=256):
+        super().__init__()
+        self.vote_aggregation = PointnetSAModuleVotes(npoint=num_proposal, radius=0.3, nsample=16,
+                                                      mlp=[seed_feat_dim, 128, 128, 128], use_xyz=True,
+                                                      normalize_xyz=True)
+
+
+class VoteNetFrontEnd(nn.Module):
+    """backbone -> votes -> L2-normalised vote features -> aggregated vote clusters."""
+
+    def __init__(self, input_feature_dim=0, num_proposal=256, vote_factor=1):
+        super().__init__()
+        self.backbone_net = Pointnet2Backbone(input_feature_dim=input_feature_dim)
+        self.vgen = VotingModule(vote_factor, 256)
+        self.proposal = _VoteAggregation(num_proposal, 256)
+
+    def forward(self, data_dict):
+        data_dict = self.backbone_net(data_dict)
+        xyz, features = data_dict["fp2_xyz"], data_dict["fp2_features"]
+        data_dict["seed_inds"] = data_dict["fp2_inds"]
+        data_dict["seed_xyz"] = xyz
+        data_dict["seed_features"] = features
+        xyz, features = self.vgen(xyz, features)
+        features_norm = torch.norm(features, p=2, dim=1)          # jointnet.py:148-149
+        features = features.div(features_norm.unsqueeze(1))
+        data_dict["vote_xyz"] = xyz
+        data_dict["vote_features"] = features
+        xyz, features, fps_inds = self.proposal.vote_aggregation(xyz, features)
+        data_dict["aggregated_vote_xyz"] = xyz
+        data_dict["aggregated_vote_features"] = features.permute(0, 2, 1).contiguous()
+        data_dict["aggregated_vote_inds"] = fps_inds
+        return data_dict

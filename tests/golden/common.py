@@ -61,3 +61,25 @@ def cloud(seed, b, n, c_extra=0, extent=2.0, dup_frac=0.0, origin_pts=0):
             where = rs.randint(0, n, size=origin_pts)
             pc[i, where, :3] = rs.uniform(-0.015, 0.015, size=(origin_pts, 3)).astype(np.float32)
     return torch.from_numpy(pc)
+
+
+def fill_state_dict_conv1d(module):
+    """Deterministic parameters for modules built from plain Conv1d / BatchNorm1d (VotingModule)."""
+    sd = module.state_dict()
+    new = {}
+    for k, v in sd.items():
+        if k.endswith("num_batches_tracked"):
+            new[k] = torch.tensor(3, dtype=v.dtype)
+        elif k.endswith("weight") and v.dim() >= 2:
+            fan_in = int(np.prod(v.shape[1:]))
+            new[k] = det_tensor(k, tuple(v.shape), scale=(2.0 / fan_in) ** 0.5 * 1.5)
+        elif k.endswith("running_var"):
+            new[k] = det_tensor(k, tuple(v.shape), scale=0.4, offset=1.0)
+        elif k.endswith("running_mean"):
+            new[k] = det_tensor(k, tuple(v.shape), scale=0.1)
+        elif k.endswith("weight"):
+            new[k] = det_tensor(k, tuple(v.shape), scale=0.2, offset=1.0)
+        else:
+            new[k] = det_tensor(k, tuple(v.shape), scale=0.1)
+    module.load_state_dict(new)
+    return new

@@ -28,7 +28,7 @@ REF = "/root/reference"
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-from common import cloud, fill_state_dict  # noqa: E402
+from common import cloud, fill_state_dict, fill_state_dict_conv1d  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 
@@ -130,6 +130,17 @@ def main():
     out["bb_fp2_features_sub"] = d["fp2_features"][:, ::8, ::16].numpy()
     out["bb_fp2_features_sum"] = np.array([d["fp2_features"].double().sum().item(),
                                            d["fp2_features"].double().abs().sum().item()])
+
+    # ---- VotingModule (models/base_module/voting_module.py, pure torch) + the L2 norm of jointnet.py ---
+    from models.base_module.voting_module import VotingModule as RefVoting
+    vm = RefVoting(1, 64)
+    fill_state_dict_conv1d(vm)
+    vm.eval()
+    sxyz = cloud(51, 2, 96, extent=1.0)[..., :3].contiguous()
+    sfeat = cloud(52, 2, 96, c_extra=61)[..., :64].transpose(1, 2).contiguous()
+    with torch.no_grad():
+        vx, vf = vm(sxyz, sfeat)
+    out["vote_xyz"], out["vote_features"] = vx.numpy(), vf.numpy()
 
     path = os.path.join(HERE, "reference_layers.npz")
     np.savez_compressed(path, **out)
