@@ -16,7 +16,7 @@ import sys as _sys
 
 from . import _lib  # noqa: F401
 from ._lib import get_option, set_option  # noqa: F401
-from . import _ext, backbone, nn_distance as _nn_distance_mod, pointnet2_modules, pointnet2_utils, pytorch_utils, voting  # noqa: F401
+from . import _ext, backbone, nn_distance as _nn_distance_mod, pointnet2_modules, pointnet2_utils, pytorch_utils, voting, loss_detection  # noqa: F401
 from .backbone import Pointnet2Backbone  # noqa: F401
 from .graph import GraphedBackbone  # noqa: F401
 from .nn_distance import huber_loss, knn_distance, nn_distance  # noqa: F401
