@@ -57,7 +57,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -239,7 +239,7 @@ def per_op_profile(torch, L, model, batch, reps=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--warmup", type=int, default=24)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -411,6 +411,28 @@ def main():
                 line["ref_cuda_ext"] = reference_cuda_ext_leg(torch, pkg, model, dev_pool, min(args.steps, 5))
             except Exception as ex:  # the baseline must never break the product's line
                 line["ref_cuda_ext"] = {"error": repr(ex)[:200]}
+        if world == 1:
+            try:  # configs[1] in full: backbone + Hough voting + vote aggregation
+                fe = pkg.VoteNetFrontEnd(input_feature_dim=C_IN)
+                fe.backbone_net = model
+                syn.randomize_bn_stats(fe.vgen); syn.randomize_bn_stats(fe.proposal)
+                fe = fe.eval().to(dev)
+                with torch.no_grad():
+                    for s in range(3):
+                        fe({"point_clouds": dev_pool[s]})
+                    torch.cuda.synchronize()
+                    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    v0.record()
+                    for s in range(20):
+                        fe({"point_clouds": dev_pool[(3 + s) % POOL]})
+                    v1.record()
+                    torch.cuda.synchronize()
+                vms = v0.elapsed_time(v1) / 20
+                line["votenet_front_end"] = {"value": SCENES_PER_GPU / (vms * 1e-3), "unit": "scenes/s", "ms_per_step": vms,
+                                             "what": "backbone + VotingModule + L2 norm + vote aggregation (256 clusters), "
+                                                     "eager, one batch in flight"}
+            except Exception as ex:
+                line["votenet_front_end"] = {"error": repr(ex)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             cores = os.cpu_count() or 1
