@@ -118,61 +118,59 @@ ball_query = BallQuery.apply
 class QueryAndGroup(nn.Module):
     """Ball query + grouping (+ recentring, optional /radius, xyz channels first).
 
-    pointnet2_utils.py:290-372, same constructor arguments and return convention.
+    pointnet2_utils.py:290-372, same constructor arguments and return convention: the grouped
+    features, then (if requested) the recentred neighbour coordinates and the per-ball unique counts.
     """
 
     def __init__(self, radius, nsample, use_xyz=True, ret_grouped_xyz=False, normalize_xyz=False,
                  sample_uniformly=False, ret_unique_cnt=False):
         super().__init__()
+        if ret_unique_cnt and not sample_uniformly:
+            raise AssertionError("ret_unique_cnt needs sample_uniformly")
         self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
         self.ret_grouped_xyz = ret_grouped_xyz
         self.normalize_xyz = normalize_xyz
         self.sample_uniformly = sample_uniformly
         self.ret_unique_cnt = ret_unique_cnt
-        if self.ret_unique_cnt:
-            assert self.sample_uniformly
+
+    def _resample_uniformly(self, idx):
+        """Replace the first-hit padding of every ball by uniform draws from its distinct members
+        (:332-341; a host loop in the reference too -- off everywhere on the hot path)."""
+        counts = torch.zeros(idx.shape[:2])
+        for b, ball_rows in enumerate(idx):
+            for j, row in enumerate(ball_rows):
+                members = torch.unique(row)
+                counts[b, j] = members.numel()
+                extra = torch.randint(0, members.numel(), (self.nsample - members.numel(),), dtype=torch.long)
+                idx[b, j] = torch.cat((members, members[extra.to(members.device)]))
+        return counts
 
     def forward(self, xyz, new_xyz, features=None):
+        """xyz (B,N,3), new_xyz (B,npoint,3), features (B,C,N) -> (B, 3 + C, npoint, nsample)."""
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        unique_cnt = self._resample_uniformly(idx) if self.sample_uniformly else None
 
-        if self.sample_uniformly:  # pointnet2_utils.py:332-341 (host loop, off on the hot path)
-            unique_cnt = torch.zeros((idx.shape[0], idx.shape[1]))
-            for i_batch in range(idx.shape[0]):
-                for i_region in range(idx.shape[1]):
-                    unique_ind = torch.unique(idx[i_batch, i_region, :])
-                    num_unique = unique_ind.shape[0]
-                    unique_cnt[i_batch, i_region] = num_unique
-                    sample_ind = torch.randint(0, num_unique, (self.nsample - num_unique,), dtype=torch.long)
-                    all_ind = torch.cat((unique_ind, unique_ind[sample_ind.to(unique_ind.device)]))
-                    idx[i_batch, i_region, :] = all_ind
-
-        xyz_trans = xyz.transpose(1, 2).contiguous()
-        grouped_xyz = grouping_operation(xyz_trans, idx)  # (B, 3, npoint, nsample)
-        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+        local = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)  # (B, 3, npoint, nsample)
+        local = local - new_xyz.transpose(1, 2).unsqueeze(-1)
         if self.normalize_xyz:
-            grouped_xyz = grouped_xyz / self.radius
+            local = local / self.radius
 
-        if features is not None:
-            grouped_features = grouping_operation(features, idx)
-            if self.use_xyz:
-                new_features = torch.cat([grouped_xyz, grouped_features], dim=1)
-            else:
-                new_features = grouped_features
-        else:
+        if features is None:
             assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
-            new_features = grouped_xyz
+            grouped = local
+        else:
+            grouped = grouping_operation(features, idx)
+            if self.use_xyz:
+                grouped = torch.cat([local, grouped], dim=1)
 
-        ret = [new_features]
-        if self.ret_grouped_xyz:
-            ret.append(grouped_xyz)
-        if self.ret_unique_cnt:
-            ret.append(unique_cnt)
-        return ret[0] if len(ret) == 1 else tuple(ret)
+        extras = ([local] if self.ret_grouped_xyz else []) + ([unique_cnt] if self.ret_unique_cnt else [])
+        return (grouped, *extras) if extras else grouped
 
 
 class GroupAll(nn.Module):
-    """pointnet2_utils.py:375-421.  (The reference forgets to store ret_grouped_xyz -- appendix C-2
-    of SURVEY.md -- so its npoint=None path raises; here the flag is kept.)"""
+    """One group holding every point (npoint=None layers): pointnet2_utils.py:375-421.  (The
+    reference forgets to store ret_grouped_xyz -- SURVEY.md appendix C-2 -- so its path raises;
+    here the flag is kept.)"""
 
     def __init__(self, use_xyz=True, ret_grouped_xyz=False):
         super().__init__()
@@ -180,12 +178,11 @@ class GroupAll(nn.Module):
         self.ret_grouped_xyz = ret_grouped_xyz
 
     def forward(self, xyz, new_xyz, features=None):
-        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
-        if features is not None:
-            grouped_features = features.unsqueeze(2)
-            new_features = torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz else grouped_features
+        coords = xyz.transpose(1, 2).unsqueeze(2)  # (B, 3, 1, N)
+        if features is None:
+            out = coords
         else:
-            new_features = grouped_xyz
-        if self.ret_grouped_xyz:
-            return new_features, grouped_xyz
-        return new_features
+            out = features.unsqueeze(2)
+            if self.use_xyz:
+                out = torch.cat([coords, out], dim=1)
+        return (out, coords) if self.ret_grouped_xyz else out
