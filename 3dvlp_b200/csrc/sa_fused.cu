@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   const uint32_t w2_bytes = static_cast<uint32_t>(C2) * C1 * 2, w3_bytes = static_cast<uint32_t>(C3) * C2 * 2;
   const uint32_t x_bytes = 128u * static_cast<uint32_t>(C1 > C2 ? C1 : C2) * 2u;
   const uint32_t s_w2 = base, s_w3 = base + w2_bytes, s_x = base + w2_bytes + w3_bytes + grp * x_bytes;  // 1 KB multiples
-  const uint32_t group_cols = (C3 > 128 || C2 > 128) ? 256u : 128u;
-  const uint32_t tmem_cols = group_cols * NG;
+  constexpr uint32_t group_cols = 128u;  // D2 (C2 <= 128 columns) and each 128-channel half of D3
+  const uint32_t tmem_cols = group_cols * NG < 32u ? 32u : group_cols * NG;
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
@@ -223,47 +223,50 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     fence_proxy_async_smem();
     tc::fence_before_sync();
     group_sync();
-    // ---------------- layer 3 (transposed): D3[h] = W3[h*128 .. +128] . X2^T -------------------
-    if (tid == 0) {
-      tc::fence_after_sync();
-      for (int h = 0; h < C3 / 128; ++h) {
+    // ---------------- layer 3 (transposed), one 128-channel half at a time ----------------------
+    // D3[h] = W3[h*128 .. +128] . X2^T always lands in the group's first 128 TMEM columns (aliasing D2),
+    // so a group needs 128 columns whatever C3 is and up to four groups share an SM.
+    for (int h = 0; h < C3 / 128 && !failed; ++h) {
+      if (h > 0) {  // every warp of the group has drained half h-1 from TMEM before it is overwritten
+        tc::fence_before_sync();
+        group_sync();
+      }
+      if (tid == 0) {
+        tc::fence_after_sync();
         for (int kk = 0; kk < C2 / 16; ++kk) {
           const uint32_t po = (kk >> 2), ko = (kk & 3) * 32;
-          tc::mma_bf16(tmem_d + h * 128,
+          tc::mma_bf16(tmem_d,
                        tc::smem_desc_sw128(s_w3 + po * (static_cast<uint32_t>(C3) * 128u) + h * (128u * 128u) + ko),
                        tc::smem_desc_sw128(s_x + po * (128u * 128u) + ko), idesc3, kk > 0 ? 1u : 0u);
         }
+        tc::mma_commit(&bar_mma);
       }
-      tc::mma_commit(&bar_mma);
-    }
-    if (!mbar_wait(&bar_mma, phase)) { failed = true; break; }
-    phase ^= 1;
-    tc::fence_after_sync();
-    // ---------------- epilogue 3: thread = channel; max over each centre's ns columns ----------
-    {
+      if (!mbar_wait(&bar_mma, phase)) { failed = true; break; }
+      phase ^= 1;
+      tc::fence_after_sync();
+      // ---- epilogue 3: thread = channel; max over each centre's ns columns ----------------------
       const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
       const int groups = 128 / ns;
-      for (int h = 0; h < C3 / 128; ++h) {
-        const int ch = h * 128 + tid;
-        const float bias = s_b3[ch];
-        for (int gidx = 0; gidx < groups; ++gidx) {
-          float mx = -INFINITY;
-          for (int c0 = 0; c0 < ns; c0 += 16) {
-            float v[16];
-            tc::tmem_ld16(lane_base + h * 128 + gidx * ns + c0, v);
+      const int ch = h * 128 + tid;
+      const float bias = s_b3[ch];
+      for (int gidx = 0; gidx < groups; ++gidx) {
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < ns; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(lane_base + gidx * ns + c0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
-          }
-          const long long jg = r0 / ns + gidx;  // global centre index
-          if (jg * ns < a.total_rows) {
-            const float o = fmaxf(mx + bias, 0.f);
-            const long long b = jg / a.npoint, j = jg - b * a.npoint;
-            a.out_cm[(b * C3 + ch) * a.npoint + j] = o;
-            if (a.out_pm) a.out_pm[jg * C3 + ch] = __float2bfloat16_rn(o);
-          }
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+        }
+        const long long jg = r0 / ns + gidx;  // global centre index
+        if (jg * ns < a.total_rows) {
+          const float o = fmaxf(mx + bias, 0.f);
+          const long long b = jg / a.npoint, j = jg - b * a.npoint;
+          a.out_cm[(b * C3 + ch) * a.npoint + j] = o;
+          if (a.out_pm) a.out_pm[jg * C3 + ch] = __float2bfloat16_rn(o);
         }
       }
     }
+    if (failed) break;
     tc::fence_before_sync();  // ordered before the next tile's __syncthreads / MMA into the same TMEM
   }
   if (failed && tid == 0) atomicExch(a.err, 2);
@@ -324,17 +327,27 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
   const size_t w_bytes = static_cast<size_t>(c2) * c1 * 2 + static_cast<size_t>(c3) * c2 * 2;
   const size_t x_bytes = 128 * static_cast<size_t>(c1 > c2 ? c1 : c2) * 2;
   const long long tiles = (a.total_rows + 127) / 128;
-  const int tm_cols = (c3 > 128 || c2 > 128) ? 256 : 128;
-  // small weight sets: several independent 128-thread CTAs per SM; big ones: one CTA with two groups
+  // Groups per CTA: as many independent 128-thread groups (own tile, own 128 TMEM columns) as shared
+  // memory allows, up to 4 (4 x 128 = all 512 TMEM columns).  Small weight sets that would fit several
+  // CTAs per SM anyway keep one group per CTA.
+  const size_t limit = 227 * 1024 - 2048;  // leave room for the static shared memory
   const size_t smem1 = w_bytes + x_bytes + 1024;
-  const int per_sm1 = smem1 <= 56 * 1024 ? 4 : (smem1 <= 113 * 1024 ? 2 : 1);
-  const int ng = (per_sm1 == 1 && tm_cols * 2 <= 512 && w_bytes + 2 * x_bytes + 1024 <= 227 * 1024) ? 2 : 1;
+  int ng = 1, resident = 1;
+  if (smem1 <= 56 * 1024) {
+    resident = 4;  // four single-group CTAs per SM (SA1-sized weights)
+  } else {
+    ng = 4;
+    while (ng > 1 && w_bytes + ng * x_bytes + 1024 > limit) ng >>= 1;
+    if (ng == 1 && smem1 <= 113 * 1024) resident = 2;
+  }
   const size_t smem = w_bytes + ng * x_bytes + 1024;
-  const int per_sm_tm = 512 / (tm_cols * ng);
-  const int resident = ng == 2 ? 1 : (per_sm1 < per_sm_tm ? per_sm1 : per_sm_tm);
   long long grid = static_cast<long long>(sm_count()) * resident;
   if (grid * ng > tiles) grid = (tiles + ng - 1) / ng;
   cudaStream_t s = as_stream(stream);
+  if (ng == 4) {
+    if (c1 == 128) return launch_cd<4, 4>(c_direct, a, static_cast<int>(grid), smem, s);
+    return launch_cd<2, 4>(c_direct, a, static_cast<int>(grid), smem, s);
+  }
   if (ng == 2) {
     if (c1 == 128) return launch_cd<4, 2>(c_direct, a, static_cast<int>(grid), smem, s);
     return launch_cd<2, 2>(c_direct, a, static_cast<int>(grid), smem, s);
