@@ -46,7 +46,7 @@ def gather_points(points, idx):
     L.require_cuda_path(points); L.check_cuda(idx, "idx")
     b, c, n = points.shape
     m = idx.size(1)
-    out = torch.zeros(b, c, m, device=points.device, dtype=torch.float32)
+    out = torch.empty(b, c, m, device=points.device, dtype=torch.float32)  # every element is written
     L.call("pn2_gather_points", b, c, n, m, L.ptr(points), L.ptr(idx), L.ptr(out), L.stream_of(points),
            device=points.device)
     return out
@@ -84,7 +84,9 @@ def group_points(points, idx):
     L.require_cuda_path(points); L.check_cuda(idx, "idx")
     b, c, n = points.shape
     m, s = idx.size(1), idx.size(2)
-    out = torch.zeros(b, c, m, s, device=points.device, dtype=torch.float32)
+    # the reference zero-fills (group_points.cpp:27-29) and then overwrites every element; skipping the
+    # fill saves a full pass over the largest tensor of the SA module
+    out = torch.empty(b, c, m, s, device=points.device, dtype=torch.float32)
     L.call("pn2_group_points", b, c, n, m, s, L.ptr(points), L.ptr(idx), L.ptr(out), L.stream_of(points),
            device=points.device)
     return out
@@ -123,7 +125,7 @@ def three_interpolate(points, idx, weight):
     L.require_cuda_path(points); L.check_cuda(idx, "idx"); L.check_cuda(weight, "weight")
     b, c, m = points.shape
     n = idx.size(1)
-    out = torch.zeros(b, c, n, device=points.device, dtype=torch.float32)
+    out = torch.empty(b, c, n, device=points.device, dtype=torch.float32)  # every element is written
     L.call("pn2_three_interpolate", b, c, m, n, L.ptr(points), L.ptr(idx), L.ptr(weight), L.ptr(out),
            L.stream_of(points), device=points.device)
     return out

@@ -3,9 +3,11 @@
 //
 // Reference path (pointnet2_modules.py:393-412): three_nn kernel -> sqrt -> 1/(d+1e-8) -> sum -> div
 // (4 torch kernels) -> three_interpolate kernel -> torch.cat -> unsqueeze -> cuDNN 1x1 convs.  Here a
-// CTA owns 32 unknown points: warp 0 finds the three nearest known points (known xyz staged in
-// shared memory, the strict-`<` cascade of interpolate_gpu.cu:39-55 so ties keep the earlier index)
-// and the weights; then all warps interpolate 64 channels at a time (lane = point, so the skip
+// CTA owns 32 unknown points and 128 channels of the output: its four warps find the three nearest
+// known points (known xyz staged in shared memory; the strict-`<` cascade of interpolate_gpu.cu:39-55
+// per quarter, merged by (distance, index) so ties keep the earlier index) and the weights -- the
+// search is cheap enough to repeat per channel block, which buys 4x the CTAs for a launch that is
+// otherwise latency-bound -- then interpolate 64 channels at a time (lane = point, so the skip
 // features are read coalesced from the reference's (B, C, n) layout), transpose through shared
 // memory and store 128-byte row segments of  X[b*n + j][0 : C2 + C1]  in bf16 -- the K-major
 // activation matrix that pn2_linear_bf16 (tcgen05) consumes.  Interpolated channels come first,
@@ -16,13 +18,26 @@ namespace pn2 {
 namespace {
 
 constexpr int FP_THREADS = 128;
-constexpr int FP_KTILE = 1024;  // known points staged per pass (12 KB)
+constexpr int FP_KTILE = 1024;  // known points staged per pass (16 KB as float4)
+constexpr int FP_CH_PER_CTA = 128;  // channels of X one CTA writes (grid.z splits the K dimension)
+
+// (d, i) ordered lexicographically: the order in which the reference's strict-`<` cascade over
+// ascending indices ranks candidates (an equal distance never displaces an earlier index).
+__device__ __forceinline__ bool before(float d, int i, float bd, int bi) { return d < bd || (d == bd && i < bi); }
+
+__device__ __forceinline__ void insert3(float d, int i, float& b1, float& b2, float& b3, int& i1, int& i2, int& i3) {
+  if (before(d, i, b1, i1)) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = i; }
+  else if (before(d, i, b2, i2)) { b3 = b2; i3 = i2; b2 = d; i2 = i; }
+  else if (before(d, i, b3, i3)) { b3 = d; i3 = i; }
+}
 
 __global__ void __launch_bounds__(FP_THREADS)
 fp_prepare_kernel(int n, int m, int c1, int c2, int kpad, const float* __restrict__ unknown,
                   const float* __restrict__ known, const float* __restrict__ uf, const float* __restrict__ kf,
                   __nv_bfloat16* __restrict__ out) {
-  __shared__ float sk[FP_KTILE * 3];
+  __shared__ float4 sk[FP_KTILE];
+  __shared__ float s_b[4][32][3];
+  __shared__ int s_i[4][32][3];
   __shared__ int s_idx[32][3];
   __shared__ float s_w[32][3];
   __shared__ float tile[32][65];
@@ -34,26 +49,39 @@ fp_prepare_kernel(int n, int m, int c1, int c2, int kpad, const float* __restric
   const float* ufb = uf ? uf + static_cast<size_t>(scene) * c1 * n : nullptr;
 
   // ---- three nearest known points + weights for the CTA's 32 unknown points --------------------
+  // lane = unknown point; the four warps each scan a quarter of every staged tile of known points
+  // and warp 0 merges the four sorted triples by (distance, index).
   const int j = p0 + lane;
   float ux = 0.f, uy = 0.f, uz = 0.f;
-  if (warp == 0 && j < n) { ux = __ldg(unknown + 3 * j); uy = __ldg(unknown + 3 * j + 1); uz = __ldg(unknown + 3 * j + 2); }
+  if (j < n) { ux = __ldg(unknown + 3 * j); uy = __ldg(unknown + 3 * j + 1); uz = __ldg(unknown + 3 * j + 2); }
   float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
   int i1 = 0, i2 = 0, i3 = 0;
   for (int t0 = 0; t0 < m; t0 += FP_KTILE) {
     const int tn = min(FP_KTILE, m - t0);
     __syncthreads();
-    for (int q = tid; q < tn * 3; q += FP_THREADS) sk[q] = __ldg(known + 3 * t0 + q);
+    for (int q = tid; q < tn; q += FP_THREADS)
+      sk[q] = make_float4(__ldg(known + 3 * (t0 + q)), __ldg(known + 3 * (t0 + q) + 1), __ldg(known + 3 * (t0 + q) + 2), 0.f);
     __syncthreads();
-    if (warp == 0 && j < n) {
-      for (int k = 0; k < tn; ++k) {
-        const float d = sqdist3(ux - sk[3 * k], uy - sk[3 * k + 1], uz - sk[3 * k + 2]);
+    const int quarter = (tn + 3) >> 2;
+    const int k_end = min(tn, (warp + 1) * quarter);
+    for (int k = warp * quarter; k < k_end; ++k) {
+      const float4 p = sk[k];
+      const float d = sqdist3(ux - p.x, uy - p.y, uz - p.z);
+      if (d < b3) {  // b1 <= b2 <= b3 always: one compare rejects almost every candidate
         if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = t0 + k; }
         else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = t0 + k; }
-        else if (d < b3) { b3 = d; i3 = t0 + k; }
+        else { b3 = d; i3 = t0 + k; }
       }
     }
   }
+  s_b[warp][lane][0] = b1; s_b[warp][lane][1] = b2; s_b[warp][lane][2] = b3;
+  s_i[warp][lane][0] = i1; s_i[warp][lane][1] = i2; s_i[warp][lane][2] = i3;
+  __syncthreads();
   if (warp == 0) {
+#pragma unroll
+    for (int w = 1; w < 4; ++w)
+#pragma unroll
+      for (int t = 0; t < 3; ++t) insert3(s_b[w][lane][t], s_i[w][lane][t], b1, b2, b3, i1, i2, i3);
     // pointnet2_utils.py:138-140 (sqrt) and pointnet2_modules.py:395-397 (1/(d+1e-8), normalise)
     const float r1 = __fdiv_rn(1.0f, __fsqrt_rn(b1) + 1e-8f), r2 = __fdiv_rn(1.0f, __fsqrt_rn(b2) + 1e-8f),
                 r3 = __fdiv_rn(1.0f, __fsqrt_rn(b3) + 1e-8f);
@@ -67,8 +95,9 @@ fp_prepare_kernel(int n, int m, int c1, int c2, int kpad, const float* __restric
   const bool live = j < n;
 
   // ---- 64 channels per pass: lane = point, warp = 16-channel slice; transpose; store ----------
-  for (int ch0 = 0; ch0 < kpad; ch0 += 64) {
-#pragma unroll 4
+  const int ch_begin = blockIdx.z * FP_CH_PER_CTA, ch_stop = min(kpad, ch_begin + FP_CH_PER_CTA);
+  for (int ch0 = ch_begin; ch0 < ch_stop; ch0 += 64) {
+#pragma unroll
     for (int cc = 0; cc < 16; ++cc) {
       const int c = ch0 + warp * 16 + cc;
       float v = 0.f;
@@ -110,7 +139,7 @@ extern "C" int pn2_fp_prepare(int b, int n, int m, int c1, int c2, int kpad, con
   PN2_REQUIRE(m > 0 && c2 > 0 && c1 >= 0 && kpad >= c1 + c2 && kpad % 64 == 0, "fp_prepare: bad sizes");
   PN2_REQUIRE(unknown && known && known_feats && out_bf16 && (c1 == 0 || unknow_feats) && b <= 65535,
               "fp_prepare: bad arguments");
-  dim3 grid((n + 31) / 32, b);
+  dim3 grid((n + 31) / 32, b, (kpad + FP_CH_PER_CTA - 1) / FP_CH_PER_CTA);
   fp_prepare_kernel<<<grid, FP_THREADS, 0, as_stream(stream)>>>(n, m, c1, c2, kpad, unknown, known, unknow_feats,
                                                                known_feats, static_cast<__nv_bfloat16*>(out_bf16));
   PN2_CHECK_LAUNCH("fp_prepare_kernel");

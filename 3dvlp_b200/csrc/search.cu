@@ -77,46 +77,64 @@ ball_query_kernel(int n, int m, float radius2, int nsample, const float* __restr
 }
 
 constexpr int NN_THREADS = 128;
-constexpr int NN_TILE = 1024;  // known points per shared-memory tile (12 KB)
+constexpr int NN_TILE = 1024;  // known points per shared-memory tile (16 KB as float4)
 
+// U unknown points per thread: one broadcast LDS.128 of a known point feeds U distance tests.
+template <int U>
 __global__ void __launch_bounds__(NN_THREADS)
 three_nn_kernel(int n, int m, const float* __restrict__ unknown, const float* __restrict__ known,
                 float* __restrict__ dist2, int* __restrict__ idx) {
-  __shared__ float sk[NN_TILE * 3];
+  __shared__ float4 sk[NN_TILE];
   const int scene = blockIdx.y;
   unknown += static_cast<size_t>(scene) * n * 3;
   known += static_cast<size_t>(scene) * m * 3;
   dist2 += static_cast<size_t>(scene) * n * 3;
   idx += static_cast<size_t>(scene) * n * 3;
-  const int j = blockIdx.x * NN_THREADS + threadIdx.x;
-  const bool live = j < n;
-  float ux = 0.f, uy = 0.f, uz = 0.f;
-  if (live) { ux = __ldg(unknown + 3 * j); uy = __ldg(unknown + 3 * j + 1); uz = __ldg(unknown + 3 * j + 2); }
+  float ux[U], uy[U], uz[U];
   // interpolate_gpu.cu:32-33 keeps doubles initialised to 1e40; a float compared after promotion
   // orders exactly like the float itself, and (float)1e40 == +inf is what an unfilled slot stores.
-  float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
-  int i1 = 0, i2 = 0, i3 = 0;
+  float b1[U], b2[U], b3[U];
+  int i1[U], i2[U], i3[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int j = (blockIdx.x * U + u) * NN_THREADS + threadIdx.x;
+    const bool live = j < n;
+    ux[u] = live ? __ldg(unknown + 3 * j) : 0.f;
+    uy[u] = live ? __ldg(unknown + 3 * j + 1) : 0.f;
+    uz[u] = live ? __ldg(unknown + 3 * j + 2) : 0.f;
+    b1[u] = b2[u] = b3[u] = INFINITY;
+    i1[u] = i2[u] = i3[u] = 0;
+  }
   for (int t0 = 0; t0 < m; t0 += NN_TILE) {
     const int tn = min(NN_TILE, m - t0);
     __syncthreads();
-    for (int q = threadIdx.x; q < tn * 3; q += NN_THREADS) sk[q] = __ldg(known + 3 * t0 + q);
+    for (int q = threadIdx.x; q < tn; q += NN_THREADS)
+      sk[q] = make_float4(__ldg(known + 3 * (t0 + q)), __ldg(known + 3 * (t0 + q) + 1), __ldg(known + 3 * (t0 + q) + 2), 0.f);
     __syncthreads();
-    if (live) {
-      for (int k = 0; k < tn; ++k) {
-        const float d = sqdist3(ux - sk[3 * k], uy - sk[3 * k + 1], uz - sk[3 * k + 2]);
-        if (d < b1) {
-          b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = t0 + k;
-        } else if (d < b2) {
-          b3 = b2; i3 = i2; b2 = d; i2 = t0 + k;
-        } else if (d < b3) {
-          b3 = d; i3 = t0 + k;
+    for (int k = 0; k < tn; ++k) {
+      const float4 p = sk[k];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float d = sqdist3(ux[u] - p.x, uy[u] - p.y, uz[u] - p.z);
+        if (d < b3[u]) {  // b1 <= b2 <= b3 always: one compare rejects almost every candidate
+          if (d < b1[u]) {
+            b3[u] = b2[u]; i3[u] = i2[u]; b2[u] = b1[u]; i2[u] = i1[u]; b1[u] = d; i1[u] = t0 + k;
+          } else if (d < b2[u]) {
+            b3[u] = b2[u]; i3[u] = i2[u]; b2[u] = d; i2[u] = t0 + k;
+          } else {
+            b3[u] = d; i3[u] = t0 + k;
+          }
         }
       }
     }
   }
-  if (live) {
-    dist2[3 * j] = b1; dist2[3 * j + 1] = b2; dist2[3 * j + 2] = b3;
-    idx[3 * j] = i1; idx[3 * j + 1] = i2; idx[3 * j + 2] = i3;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int j = (blockIdx.x * U + u) * NN_THREADS + threadIdx.x;
+    if (j < n) {
+      dist2[3 * j] = b1[u]; dist2[3 * j + 1] = b2[u]; dist2[3 * j + 2] = b3[u];
+      idx[3 * j] = i1[u]; idx[3 * j + 1] = i2[u]; idx[3 * j + 2] = i3[u];
+    }
   }
 }
 
@@ -151,8 +169,14 @@ extern "C" int pn2_three_nn(int b, int n, int m, const float* unknown, const flo
   if (b <= 0 || n <= 0) return PN2_OK;
   PN2_REQUIRE(m >= 0 && unknown && dist2 && idx && (known || m == 0), "three_nn: bad arguments");
   PN2_REQUIRE(b <= 65535, "three_nn: batch %d exceeds the grid limit", b);
-  dim3 grid((n + NN_THREADS - 1) / NN_THREADS, b);
-  three_nn_kernel<<<grid, NN_THREADS, 0, as_stream(stream)>>>(n, m, unknown, known, dist2, idx);
+  // two unknowns per thread once there are enough of them to fill the machine twice over
+  if (static_cast<long long>(n) * b >= 4LL * sm_count() * NN_THREADS * 2) {
+    dim3 grid((n + 2 * NN_THREADS - 1) / (2 * NN_THREADS), b);
+    three_nn_kernel<2><<<grid, NN_THREADS, 0, as_stream(stream)>>>(n, m, unknown, known, dist2, idx);
+  } else {
+    dim3 grid((n + NN_THREADS - 1) / NN_THREADS, b);
+    three_nn_kernel<1><<<grid, NN_THREADS, 0, as_stream(stream)>>>(n, m, unknown, known, dist2, idx);
+  }
   PN2_CHECK_LAUNCH("three_nn_kernel");
   return PN2_OK;
 }

@@ -189,6 +189,49 @@ def test_three_interpolate(pkg, oracle, cuda, c):
                                oracle.ext.three_interpolate_grad(go, idx, w, m), rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("n,m,ns,c", [(40000, 2048, 64, 5), (39999, 1000, 33, 3), (2048, 1024, 32, 131), (57000, 512, 16, 2),
+                                      (60000, 512, 16, 2)])
+def test_group_points_staged_rows(pkg, cuda, n, m, ns, c):
+    """Rows re-used often enough are gathered out of shared memory (TMA-staged when 16-byte aligned,
+    plain loads otherwise; n = 60000 no longer fits and takes the direct kernel): pure copies, so the
+    result must equal torch's own gather bit for bit; the scatter-add gradient is compared with
+    index_add_ within the fp32 summation-order tolerance."""
+    g = torch.Generator().manual_seed(n + c)
+    pts = torch.randn(2, c, n, generator=g).to(cuda)
+    idx = torch.randint(0, n, (2, m, ns), generator=g, dtype=torch.int32)
+    idx[:, ::3, ns // 4:] = idx[:, ::3, :1]  # ball-query style padding: long runs of one index
+    idx = idx.to(cuda)
+    got = pkg._ext.group_points(pts, idx)
+    flat = idx.view(2, 1, m * ns).long().expand(-1, c, -1)
+    assert torch.equal(got, torch.gather(pts, 2, flat).view(2, c, m, ns))
+    go = torch.randn(2, c, m, ns, generator=g).to(cuda)
+    want = torch.zeros(2, c, n, device=cuda).scatter_add_(2, flat, go.view(2, c, -1))
+    torch.testing.assert_close(pkg._ext.group_points_grad(go, idx, n), want, rtol=1e-4, atol=1e-4)
+    # gather_points with many samples takes the same staged kernel
+    gi = idx[:, :, 0].contiguous() if m * 2 >= n else idx.view(2, -1)[:, : (n // 2 + 7)].contiguous()
+    gg = pkg._ext.gather_points(pts, gi)
+    assert torch.equal(gg, torch.gather(pts, 2, gi.long().unsqueeze(1).expand(-1, c, -1)))
+    go2 = torch.randn(2, c, gi.shape[1], generator=g).to(cuda)
+    want2 = torch.zeros(2, c, n, device=cuda).scatter_add_(2, gi.long().unsqueeze(1).expand(-1, c, -1), go2)
+    torch.testing.assert_close(pkg._ext.gather_points_grad(go2, gi, n), want2, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("c,m,n", [(37, 2048, 9000), (256, 512, 1024), (3, 100, 150), (8, 7000, 20000), (64, 300, 1201)])
+def test_three_interpolate_staged_tiles(pkg, oracle, cuda, c, m, n):
+    """Channel-tiled shared-memory interpolation (tile widths 32/16/8/4 by size, direct kernel when
+    n < 2m or the known set is too large): bit-exact against the oracle's fma chain."""
+    g = torch.Generator().manual_seed(c + n)
+    feats = torch.randn(2, c, m, generator=g)
+    idx = torch.randint(0, m, (2, n, 3), generator=g, dtype=torch.int32)
+    w = torch.rand(2, n, 3, generator=g)
+    w = w / w.sum(-1, keepdim=True)
+    got = pkg._ext.three_interpolate(feats.to(cuda), idx.to(cuda), w.to(cuda)).cpu()
+    assert torch.equal(got, oracle.ext.three_interpolate(feats, idx, w))
+    go = torch.randn(2, c, n, generator=g)
+    torch.testing.assert_close(pkg._ext.three_interpolate_grad(go.to(cuda), idx.to(cuda), w.to(cuda), m).cpu(),
+                               oracle.ext.three_interpolate_grad(go, idx, w, m), rtol=1e-4, atol=1e-4)
+
+
 NND_SHAPES = [(1, 5, 6, 3), (3, 37, 23, 3), (64, 1, 3, 3), (4, 256, 256, 3), (16, 256, 1, 3), (2, 40, 50, 6),
               (2, 1500, 1300, 3)]
 
