@@ -356,7 +356,13 @@ def main():
 
     if rank == 0:
         hbm_peak, tensor_peak, peak_kind = peaks()
-        ops = per_op_profile(torch, L, model, dev_pool[1])
+        # profile the calls with the FPS variant the timed graphs captured
+        prev_opt = L.get_option("fps_bucket")
+        L.set_option("fps_bucket", 1 if throughput_mode else 0)
+        try:
+            ops = per_op_profile(torch, L, model, dev_pool[1])
+        finally:
+            L.set_option("fps_bucket", prev_opt)
         step_ms = ms / args.steps
         # dominant kernel: the SA1 furthest-point sampling call (first FPS call of the forward)
         fps_key = next((k for k in ops if k[0].startswith("pn2_furthest_point_sampling") and k[1] == 0), None)
@@ -370,8 +376,10 @@ def main():
             traffic = None
             tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
             if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
-                traffic = json.load(open(tp)).get("fps_kernel_sa1_bytes_per_launch")
-            roofline = {"kernel": "fps_kernel (SA1, 40000->2048)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                traffic = json.load(open(tp)).get(
+                    "fps_bucket_kernel_sa1_bytes_per_launch" if throughput_mode else "fps_kernel_sa1_bytes_per_launch")
+            roofline = {"kernel": ("fps_bucket_kernel" if throughput_mode else "fps_kernel") + " (SA1, 40000->2048)",
+                        "bound": "hbm", "achieved": ach, "peak": hbm_peak,
                         "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
                         "ms": ops[fps_key], "share_of_forward": ops[fps_key] / sum(ops.values()),
                         "note": "FPS is latency/ALU-bound by construction (2047 dependent rounds); see alu_frac",

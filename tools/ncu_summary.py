@@ -45,10 +45,12 @@ def main():
             blocks.append(cur)
         elif cur is not None:
             cur["rows"].append(r)
-    for b in blocks[:8]:
+    done = set()
+    for b in blocks:
         rows = b["rows"]
-        if not rows:
+        if not rows or b["name"] in done or len(done) >= 8:
             continue
+        done.add(b["name"])  # one stall table per kernel (repeat launches of one kernel look alike)
         hdr = rows[0]
         try:
             isrc, isamp, iex = hdr.index("Source"), hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")
