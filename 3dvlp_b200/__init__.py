@@ -16,12 +16,13 @@ import sys as _sys
 
 from . import _lib  # noqa: F401
 from ._lib import get_option, set_option  # noqa: F401
-from . import _ext, backbone, nn_distance as _nn_distance_mod, pointnet2_modules, pointnet2_utils, pytorch_utils, voting, loss_detection  # noqa: F401
+from . import _ext, backbone, nn_distance as _nn_distance_mod, pointnet2_modules, pointnet2_utils, pytorch_utils, voting, loss_detection, box_util, loss_grounding, contrast  # noqa: F401
 from .backbone import Pointnet2Backbone  # noqa: F401
 from .graph import GraphedBackbone  # noqa: F401
 from .nn_distance import huber_loss, knn_distance, nn_distance  # noqa: F401
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes  # noqa: F401
 from .voting import VoteNetFrontEnd, VotingModule  # noqa: F401
+from .contrast import ContrastModule  # noqa: F401
 
 __all__ = ["Pointnet2Backbone", "GraphedBackbone", "VotingModule", "VoteNetFrontEnd", "PointnetSAModuleVotes", "PointnetFPModule", "nn_distance", "huber_loss",
            "knn_distance", "pointnet2_utils", "pointnet2_modules", "pytorch_utils", "install_dropin"]

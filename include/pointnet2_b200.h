@@ -134,6 +134,34 @@ int pn2_nn_distance_grad(int b, int n, int m, int c, const float* pc1, const flo
                          float* grad_pc2, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Axis-aligned box IoU / DIoU -- utils/box_util.py:488-528 `box3d_diou_batch_tensor` (element-wise
+ * torch ops in the reference, driven by Python loops in lib/loss_helper/loss_grounding.py:205-231)
+ * and the axis-aligned use of pytorch3d `box3d_overlap` in
+ * models/constrast_module/constrast_module.py:105.  SURVEY.md 8f ranks 3-4.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Boxes as centre + size, fp32 (.,3).  box1 = (b,k) proposals, box2 = (b,l) targets ->
+ * iou / diou (b,l,k) (either output may be NULL).  Bit-identical to the reference's fp32 op tree.
+ * The element-wise form of the reference (P independent pairs) is the call b=P, l=1, k=1. */
+int pn2_box3d_diou_pairs(int b, int l, int k, const float* center1, const float* size1,
+                         const float* center2, const float* size2, float* iou, float* diou,
+                         void* stream);
+
+/* Gradient w.r.t. the proposals, summed over the l targets: grad_iou / grad_diou (b,l,k) (either
+ * may be NULL) -> grad_center1, grad_size1 (b,k,3), overwritten.  torch's tie rules for
+ * max/min/clamp. */
+int pn2_box3d_diou_pairs_grad(int b, int l, int k, const float* center1, const float* size1,
+                              const float* center2, const float* size2, const float* grad_iou,
+                              const float* grad_diou, float* grad_center1, float* grad_size1,
+                              void* stream);
+
+/* Element-wise gradient for both boxes (P pairs); any grad output may be NULL. */
+int pn2_box3d_diou_grad(long long p, const float* center1, const float* size1, const float* center2,
+                        const float* size2, const float* grad_iou, const float* grad_diou,
+                        float* grad_center1, float* grad_size1, float* grad_center2,
+                        float* grad_size2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * SharedMLP on tcgen05 tensor cores -- pytorch_utils.py:11-36 (Conv2d 1x1 -> BatchNorm2d -> ReLU;
  * cuDNN in the reference).  BatchNorm (eval) is folded into W / bias by the host layer.
  * ------------------------------------------------------------------------------------------- */
