@@ -178,6 +178,24 @@ pack_rows_kernel(int c, int n, int kpad, const float* __restrict__ f, __nv_bfloa
   }
 }
 
+// point-major rows of the input cloud, (rows, ld) fp32 with the features in columns [col0, col0+c),
+// -> (rows, kpad) bf16 zero padded: thread = 8 output channels (one 16-byte store)
+__global__ void __launch_bounds__(256)
+pack_point_rows_kernel(long long rows, int ld, int col0, int c, int kpad, const float* __restrict__ in,
+                       __nv_bfloat16* __restrict__ out) {
+  const int chunks = kpad >> 3;
+  const long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (t >= rows * chunks) return;
+  const long long r = t / chunks;
+  const int ch0 = static_cast<int>(t - r * chunks) << 3;
+  const float* src = in + r * ld + col0 + ch0;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = ch0 + i < c ? __ldg(src + i) : 0.f;
+  *reinterpret_cast<uint4*>(out + r * kpad + ch0) = make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]),
+                                                               tc::pack_bf16(v[4], v[5]), tc::pack_bf16(v[6], v[7]));
+}
+
 }  // namespace
 
 int* device_err_flag();  // defined in abi.cu
@@ -199,6 +217,18 @@ extern "C" int pn2_pack_rows_bf16(int b, int c, int n, int kpad, const float* fe
   dim3 grid((n + 31) / 32, (kpad + 31) / 32, b);
   pack_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(c, n, kpad, features, static_cast<__nv_bfloat16*>(out));
   PN2_CHECK_LAUNCH("pack_rows_kernel");
+  return PN2_OK;
+}
+
+extern "C" int pn2_pack_point_rows_bf16(long long rows, int ld, int col0, int c, int kpad, const float* in, void* out,
+                                        void* stream) {
+  if (rows <= 0) return PN2_OK;
+  PN2_REQUIRE(c > 0 && col0 >= 0 && ld >= col0 + c && kpad >= c && kpad % 8 == 0 && in && out,
+              "pack_point_rows_bf16: bad arguments");
+  const long long total = rows * (kpad / 8);
+  pack_point_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+      rows, ld, col0, c, kpad, in, static_cast<__nv_bfloat16*>(out));
+  PN2_CHECK_LAUNCH("pack_point_rows_kernel");
   return PN2_OK;
 }
 

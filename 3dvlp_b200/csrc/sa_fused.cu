@@ -136,46 +136,61 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
 #pragma unroll
         for (int d = 0; d < CD; ++d) fd[d] = __ldg(a.feat + (static_cast<size_t>(b) * CD + d) * a.N + pi);
       }
-#pragma unroll 4
-      for (int i = 0; i < 32; ++i) {
-        const float x = __shfl_sync(0xffffffffu, rx, i), y = __shfl_sync(0xffffffffu, ry, i),
-                    z = __shfl_sync(0xffffffffu, rz, i);
-        const bool rok = __shfl_sync(0xffffffffu, static_cast<int>(ok), i) != 0;
-        float v[CPL];
+      // rows in batches of GB: in gather mode the batch's g rows are all requested before the first is
+      // used (the loop is bound by that latency: 4 loads in flight per warp left the kernel stalled
+      // on `v += g` for a third of its samples)
+      constexpr int GB = CPL == 4 ? 8 : 16;
+      constexpr int GW = CPL == 4 ? 4 : 2;
+#pragma unroll 1
+      for (int i0 = 0; i0 < 32; i0 += GB) {
+        float gq[CD == 0 ? GB : 1][GW];
+        if (CD == 0 && a.g != nullptr) {  // g and raw channels are alternatives (the host picks one)
 #pragma unroll
-        for (int q = 0; q < CPL; ++q) v[q] = __fmaf_rn(wz[q], z, __fmaf_rn(wy[q], y, __fmaf_rn(wx[q], x, wb[q])));
-        if (CD > 0) {
-#pragma unroll
-          for (int d = 0; d < CD; ++d) {
-            const float f = __shfl_sync(0xffffffffu, fd[d], i);
-#pragma unroll
-            for (int q = 0; q < CPL; ++q) v[q] = __fmaf_rn(wf[q][d], f, v[q]);
-          }
-        }
-        if (a.g != nullptr) {
-          const long long gr = __shfl_sync(0xffffffffu, grow, i);
-          if (rok) {
+          for (int u = 0; u < GB; ++u) {
+            const long long gr = __shfl_sync(0xffffffffu, grow, i0 + u);  // rows past the end carry row 0
             if (CPL == 4) {
-              const float4 gv = __ldg(reinterpret_cast<const float4*>(a.g + gr * C1) + lane);
-              v[0] += gv.x; v[1] += gv.y; v[2] += gv.z; v[3] += gv.w;
+              const float4 t = __ldg(reinterpret_cast<const float4*>(a.g + gr * C1) + lane);
+              gq[CD == 0 ? u : 0][0] = t.x; gq[CD == 0 ? u : 0][1] = t.y; gq[CD == 0 ? u : 0][GW - 2] = t.z; gq[CD == 0 ? u : 0][GW - 1] = t.w;
             } else {
-              const float2 gv = __ldg(reinterpret_cast<const float2*>(a.g + gr * C1) + lane);
-              v[0] += gv.x; v[1] += gv.y;
+              const float2 t = __ldg(reinterpret_cast<const float2*>(a.g + gr * C1) + lane);
+              gq[CD == 0 ? u : 0][0] = t.x; gq[CD == 0 ? u : 0][1] = t.y;
             }
           }
         }
 #pragma unroll
-        for (int q = 0; q < CPL; ++q) v[q] = rok ? fmaxf(v[q], 0.f) : 0.f;
-        const uint32_t row = warp * 32 + i;
-        const uint32_t c0 = lane * CPL;              // first channel of this lane
-        const uint32_t chunk = c0 >> 3;               // 16-byte chunk along K
-        const uint32_t addr = s_x + (chunk >> 3) * (128u * 128u) + tc::swz_off(row, chunk & 7u) + (c0 & 7u) * 2u;
-        if (CPL == 4) {
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(tc::pack_bf16(v[0], v[1])),
-                       "r"(tc::pack_bf16(v[2], v[3]))
-                       : "memory");
-        } else {
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(tc::pack_bf16(v[0], v[1])) : "memory");
+        for (int u = 0; u < GB; ++u) {
+          const int i = i0 + u;
+          const float x = __shfl_sync(0xffffffffu, rx, i), y = __shfl_sync(0xffffffffu, ry, i),
+                      z = __shfl_sync(0xffffffffu, rz, i);
+          const bool rok = __shfl_sync(0xffffffffu, static_cast<int>(ok), i) != 0;
+          float v[CPL];
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) v[q] = __fmaf_rn(wz[q], z, __fmaf_rn(wy[q], y, __fmaf_rn(wx[q], x, wb[q])));
+          if (CD > 0) {
+#pragma unroll
+            for (int d = 0; d < CD; ++d) {
+              const float f = __shfl_sync(0xffffffffu, fd[d], i);
+#pragma unroll
+              for (int q = 0; q < CPL; ++q) v[q] = __fmaf_rn(wf[q][d], f, v[q]);
+            }
+          }
+          if (CD == 0 && a.g != nullptr) {
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) v[q] += gq[CD == 0 ? u : 0][q];
+          }
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) v[q] = rok ? fmaxf(v[q], 0.f) : 0.f;
+          const uint32_t row = warp * 32 + i;
+          const uint32_t c0 = lane * CPL;              // first channel of this lane
+          const uint32_t chunk = c0 >> 3;               // 16-byte chunk along K
+          const uint32_t addr = s_x + (chunk >> 3) * (128u * 128u) + tc::swz_off(row, chunk & 7u) + (c0 & 7u) * 2u;
+          if (CPL == 4) {
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(tc::pack_bf16(v[0], v[1])),
+                         "r"(tc::pack_bf16(v[2], v[3]))
+                         : "memory");
+          } else {
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(tc::pack_bf16(v[0], v[1])) : "memory");
+          }
         }
       }
     }
@@ -314,6 +329,7 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
   PN2_REQUIRE(xyz && new_xyz && idx && w1 && b1 && w2_packed && b2 && w3_packed && b3 && out_cm && n > 0,
               "sa_group_mlp: null pointer");
   PN2_REQUIRE(c_direct >= 0 && c_direct <= 4 && (c_direct == 0 || feat), "sa_group_mlp: bad direct features");
+  PN2_REQUIRE(!(g && c_direct > 0), "sa_group_mlp: pass either g (per-point layer-1 rows) or raw channels, not both");
   PN2_REQUIRE(radius_div != 0.f, "sa_group_mlp: radius_div must be non-zero");
   SaArgs a;
   a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx; a.g = g; a.feat = feat; a.w1 = w1; a.b1 = b1;

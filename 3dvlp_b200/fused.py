@@ -108,8 +108,10 @@ def sa_sample(module, xyz, inds=None):
     return inds, new_xyz
 
 
-def sa_features(module, plan, xyz, features, new_xyz):
-    """Ball query + (wide inputs: per-point GEMM) + the fused grouping/MLP/max-pool kernel."""
+def sa_features(module, plan, xyz, features, new_xyz, rows=None):
+    """Ball query + (wide inputs: per-point GEMM) + the fused grouping/MLP/max-pool kernel.
+    `rows`: the (B*N, kpad) bf16 point-major operand of the per-point GEMM when the caller already
+    has it (then `features` is not read)."""
     b, n = xyz.shape[0], xyz.shape[1]
     dev = xyz.device
     c_feat = 0 if features is None else features.shape[1]
@@ -120,7 +122,8 @@ def sa_features(module, plan, xyz, features, new_xyz):
         if c_feat:
             feat = features.contiguous().float()
     else:
-        rows = getattr(features, "_pn2_rows", None)
+        if rows is None:
+            rows = getattr(features, "_pn2_rows", None)
         if rows is None or rows.shape != (b * n, plan.w1f.kpad) or rows.device != dev:
             rows = tcm.pack_rows(features.contiguous().float(), plan.w1f.kpad)
         g = tcm.linear(rows, plan.w1f, None, relu=False, out="f32")
@@ -172,7 +175,15 @@ def backbone_forward(bb, data_dict):
     pc = data_dict["point_clouds"]
     if pc.dtype != torch.float32 or pc.size(-1) - 3 != plans[0].c_in:
         return None
-    xyz, features = bb._break_up_pc(pc)
+    rows1 = None
+    if plans[0].direct or plans[0].c_in == 0:
+        xyz, features = bb._break_up_pc(pc)
+    else:
+        # wide inputs (multiview features): the per-point GEMM of SA1 reads point-major rows, which is
+        # how the cloud arrives -- convert in place of _break_up_pc's transpose to (B, C, N) and back
+        pc = pc.contiguous()
+        xyz, features = pc[..., :3].contiguous(), None
+        rows1 = tcm.pack_point_rows(pc, 3, plans[0].c_in, plans[0].w1f.kpad)
     dev = xyz.device
     main = torch.cuda.current_stream(dev)
     side = _side_streams.get(dev)
@@ -196,11 +207,12 @@ def backbone_forward(bb, data_dict):
         if not capturing:  # graph-private pool memory is never handed to another stream
             inds.record_stream(main)
             new_xyz.record_stream(main)
-        c_feat = 0 if f is None else f.shape[1]
+        r = rows1 if name == "sa1" else None
+        c_feat = plan.c_in if r is not None else (0 if f is None else f.shape[1])
         if c_feat != plan.c_in:
             main.wait_stream(side)
             return None
-        f = sa_features(sa, plan, x, f, new_xyz)
+        f = sa_features(sa, plan, x, f, new_xyz, rows=r)
         x = new_xyz
         data_dict[name + "_xyz"] = x
         data_dict[name + "_features"] = f

@@ -33,6 +33,18 @@ def pack_rows(features, kpad=None):
     return out
 
 
+def pack_point_rows(pc, col0, c, kpad=None):
+    """(B, N, ld) fp32 point rows, features in columns [col0, col0+c) -> (B*N, kpad) bf16 rows."""
+    import ctypes
+    L.check_contiguous(pc, "pc"); L.check_float(pc, "pc"); L.require_cuda_path(pc)
+    b, n, ld = pc.shape
+    kpad = kpad or kpad64(c)
+    out = torch.empty(b * n, kpad, device=pc.device, dtype=torch.bfloat16)
+    L.call("pn2_pack_point_rows_bf16", ctypes.c_longlong(b * n), ld, col0, c, kpad, L.ptr(pc), L.ptr(out),
+           L.stream_of(pc), device=pc.device)
+    return out
+
+
 def linear(x, w, bias=None, relu=False, out="f32", rows_per_batch=0):
     """act(x @ W^T + bias) on tensor cores.  x (M, kpad) bf16; w PackedWeight; out in
     {"f32": (M,n) fp32, "bf16": (M,n) bf16, "cm": (M/rows_per_batch, n, rows_per_batch) fp32}."""

@@ -173,6 +173,12 @@ int pn2_pack_weight_bf16(int n, int k, int kpad, const float* w, void* out, void
 /* features (b,c,n) fp32 channel-major (the reference's feature layout) -> (b*n, kpad) bf16 rows. */
 int pn2_pack_rows_bf16(int b, int c, int n, int kpad, const float* features, void* out, void* stream);
 
+/* Rows of the input cloud as the dataset stores them -- (rows, ld) fp32, features in columns
+ * [col0, col0+c) after x,y,z (models/base_module/backbone_module.py:69-74 `_break_up_pc`) -> the same
+ * (rows, kpad) bf16 operand, without the transpose to (b,c,n) and back. */
+int pn2_pack_point_rows_bf16(long long rows, int ld, int col0, int c, int kpad, const float* in, void* out,
+                             void* stream);
+
 /* Y = act(X W^T + bias).  X (m,k) bf16 row-major, k % 64 == 0; W packed as above (n % 16 == 0,
  * n <= 256); bias (n) fp32 or NULL; relu 0/1.  out_mode 0: Y fp32 (m,n) row-major; 1: Y bf16 (m,n)
  * row-major; 2: Y fp32 channel-major (m / rows_per_batch, n, rows_per_batch) -- the reference's
