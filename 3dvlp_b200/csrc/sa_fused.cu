@@ -45,6 +45,7 @@ struct SaArgs {
   float* out_cm;         // (B, C3, npoint) fp32
   __nv_bfloat16* out_pm; // (B*npoint, C3) bf16 or nullptr
   int* err;
+  int* tile_counter;     // {next tile, finished CTAs}, both zero at launch: tiles are handed out dynamically
   int B, N, npoint, ns, C1, C2, C3;
   float radius_div;      // divisor applied to the recentred xyz (radius, or 1 when not normalised)
   long long total_rows;  // B * npoint * ns
@@ -54,11 +55,21 @@ struct SaArgs {
 // TMEM columns and mbarrier; the folded weights in shared memory are shared.  When the weights leave room
 // for only one CTA per SM (SA2-SA4: 96 KB) two groups give the SM a second tile to work on while the
 // first waits for its gather / MMA / TMEM round trips.
-template <int CPL, int CD, int NG>  // channels per lane in layer 1 (C1 = 32 * CPL), raw feature channels
+//
+// MMA1 (raw-channel mode, no g): layer 1 runs on the tensor cores too.  Its fp32 inputs
+// v = ((p - centre)/radius, raw channels) and fp32 weights are each split into THREE bf16 terms
+// (h = bf16(v), m = bf16(v - h), l = bf16(v - h - m): 24 mantissa bits); the six products whose
+// weight is >= 2^-16 of w.v  (w_h v_h, w_h v_m, w_m v_h, w_h v_l, w_l v_h, w_m v_m)  and the bias
+// (b_h + b_m + b_l against three columns of ones) become one K = 32 or 48 GEMM whose operand a thread
+// builds for its own row: ~60 instructions per row instead of ~24 per row AND lane.  Every product is
+// exact in the fp32 accumulator and the dropped terms are ~2^-24 relative, i.e. the result matches the
+// fp32 FMA chain to fp32 rounding -- the bf16 rounding that follows sees the same values.
+template <int CPL, int CD, int NG, bool MMA1>  // C1 = 32 * CPL, raw feature channels, groups, layer 1 on MMA
 __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, bar_mma_g[NG];
   __shared__ uint32_t tmem_slot;
+  __shared__ int s_next[NG][2];  // next tile of each group, double-buffered by iteration parity
   __shared__ float s_b2[128], s_b3[256];
 
   constexpr int C1 = 32 * CPL;
@@ -69,7 +80,11 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w2_bytes = static_cast<uint32_t>(C2) * C1 * 2, w3_bytes = static_cast<uint32_t>(C3) * C2 * 2;
   const uint32_t x_bytes = 128u * static_cast<uint32_t>(C1 > C2 ? C1 : C2) * 2u;
-  const uint32_t s_w2 = base, s_w3 = base + w2_bytes, s_x = base + w2_bytes + w3_bytes + grp * x_bytes;  // 1 KB multiples
+  constexpr int NT = 6 * (3 + CD) + 3;          // layer-1 product terms (MMA1): 6 per input + 3 for the bias
+  constexpr int K0 = (NT + 15) / 16 * 16;        // 32 (CD <= 1) or 48: inside the first 64-wide K panel
+  const uint32_t w1_bytes = MMA1 ? static_cast<uint32_t>(C1) * 128u : 0u;
+  const uint32_t s_w2 = base, s_w3 = base + w2_bytes, s_w1 = s_w3 + w3_bytes,
+                 s_x = s_w1 + w1_bytes + grp * x_bytes;  // 1 KB multiples
   constexpr uint32_t group_cols = 128u;  // D2 (C2 <= 128 columns) and each 128-channel half of D3
   const uint32_t tmem_cols = group_cols * NG < 32u ? 32u : group_cols * NG;
 
@@ -80,6 +95,35 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   }
   for (int i = threadIdx.x; i < C2; i += SA_THREADS * NG) s_b2[i] = a.b2[i];
   for (int i = threadIdx.x; i < C3; i += SA_THREADS * NG) s_b3[i] = a.b3[i];
+  if (MMA1) {
+    // B operand of layer 1: row = channel, K-major: [w_h, w_h, w_m, w_h, w_l, w_m] per input (against
+    // [v_h, v_m, v_h, v_l, v_h, v_m]), [b_h, b_m, b_l] against ones, zeros up to K0
+    for (int e = threadIdx.x; e < C1 * K0; e += SA_THREADS * NG) {
+      const int ch = e / K0, k = e - ch * K0;
+      float w = 0.f;
+      int part = 0;  // 0 = h, 1 = m, 2 = l
+      if (k < NT - 3) {
+        w = a.w1[static_cast<size_t>(ch) * (3 + CD) + k / 6];
+        const int t = k % 6;
+        part = t == 2 || t == 5 ? 1 : (t == 4 ? 2 : 0);
+      } else if (k < NT) {
+        w = a.b1[ch];
+        part = k - (NT - 3);
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(w);
+      const float r1 = w - __bfloat162float(h);
+      const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+      const __nv_bfloat16 val = part == 0 ? h : (part == 1 ? m : l);
+      const uint32_t addr = s_w1 + tc::swz_off(ch, static_cast<uint32_t>(k) >> 3) + (k & 7) * 2;
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__bfloat16_as_ushort(val)) : "memory");
+    }
+    fence_proxy_async_smem();
+  }
+  // Tiles come from a global counter, not from a static stride: when other kernels hold some SMs
+  // (several batches in flight) part of the grid starts late, and a late CTA must find the work
+  // already done instead of a full static share of it.
+  if (tid == 0) s_next[grp][0] = atomicAdd(a.tile_counter, 1);
   if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot, tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
@@ -97,7 +141,7 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   // layer-1 weights of this lane's channels, in registers for the whole kernel
   float wx[CPL], wy[CPL], wz[CPL], wb[CPL], wf[CPL][CD > 0 ? CD : 1];
 #pragma unroll
-  for (int q = 0; q < CPL; ++q) {
+  for (int q = 0; q < CPL && !MMA1; ++q) {
     const int c = lane * CPL + q;
     const float* row = a.w1 + static_cast<size_t>(c) * (3 + CD);
     wx[q] = row[0]; wy[q] = row[1]; wz[q] = row[2]; wb[q] = a.b1[c];
@@ -105,37 +149,121 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     for (int d = 0; d < CD; ++d) wf[q][d] = row[3 + d];
   }
 
+  const uint32_t idesc1 = tc::idesc_bf16_f32(128, C1);
   const uint32_t idesc2 = tc::idesc_bf16_f32(128, C2);
   const uint32_t idesc3 = tc::idesc_bf16_f32(128, 128);
   const long long n_tiles = (a.total_rows + 127) / 128;
   uint32_t phase = 0;
   bool weights_ready = false, failed = false;
 
-  for (long long tile = static_cast<long long>(blockIdx.x) * NG + grp; tile < n_tiles && !failed;
-       tile += static_cast<long long>(gridDim.x) * NG) {
+  // Inputs of this thread's row (row = tile * 128 + tid): neighbour index -> point coordinates, centre,
+  // raw channels.  A dependent chain of two global round trips, so the NEXT tile's inputs are requested
+  // while the current tile is still in its layer-3 epilogue.
+  float in_p[3], in_c[3], in_f[CD > 0 ? CD : 1];
+  long long in_grow = 0;
+  bool in_ok = false;
+  auto fetch_row = [&](long long t) {
+    const long long R = t * 128 + tid;
+    in_ok = t < n_tiles && R < a.total_rows;
+    in_grow = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) in_p[d] = in_c[d] = 0.f;
+#pragma unroll
+    for (int d = 0; d < (CD > 0 ? CD : 1); ++d) in_f[d] = 0.f;
+    if (in_ok) {
+      const long long jg = R / ns;  // global centre index b*npoint + j
+      const int b = static_cast<int>(jg / a.npoint);
+      const int pi = __ldg(a.idx + R);
+      in_grow = static_cast<long long>(b) * a.N + pi;  // row of g / point id within the batch-flattened cloud
+      const float* p = a.xyz + in_grow * 3;
+      const float* c = a.new_xyz + jg * 3;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { in_p[d] = __ldg(p + d); in_c[d] = __ldg(c + d); }
+#pragma unroll
+      for (int d = 0; d < CD; ++d) in_f[d] = __ldg(a.feat + (static_cast<size_t>(b) * CD + d) * a.N + pi);
+    }
+  };
+  long long tile = s_next[grp][0], next_tile = n_tiles;
+  fetch_row(tile);
+
+  for (int it = 0; tile < n_tiles && !failed; ++it, tile = next_tile) {
     const long long r0 = tile * 128;
-    // ---------------- layer 1: build X1 (bf16) for rows warp*32 .. warp*32+31 -------------------
-    {
-      const long long R = r0 + warp * 32 + lane;  // the row this lane prepares geometry for
-      const bool ok = R < a.total_rows;
-      float rx = 0.f, ry = 0.f, rz = 0.f, fd[CD > 0 ? CD : 1];
-      long long grow = 0;  // row of g / point id within the batch-flattened cloud
+    // claim the tile after this one; the group reads it after the next group_sync (the other parity
+    // slot was last read an iteration ago, several group_syncs back)
+    if (tid == 0) s_next[grp][(it + 1) & 1] = atomicAdd(a.tile_counter, 1);
+    // pointnet2_utils.py:345-348: grouped_xyz -= new_xyz; grouped_xyz /= radius  (fp32 divide)
+    const bool ok = in_ok;
+    const long long grow = in_grow;
+    const float rx = ok ? __fdiv_rn(in_p[0] - in_c[0], a.radius_div) : 0.f;
+    const float ry = ok ? __fdiv_rn(in_p[1] - in_c[1], a.radius_div) : 0.f;
+    const float rz = ok ? __fdiv_rn(in_p[2] - in_c[2], a.radius_div) : 0.f;
+    float fd[CD > 0 ? CD : 1];
 #pragma unroll
-      for (int d = 0; d < (CD > 0 ? CD : 1); ++d) fd[d] = 0.f;
-      if (ok) {
-        const long long jg = R / ns;  // global centre index b*npoint + j
-        const int b = static_cast<int>(jg / a.npoint);
-        const int pi = __ldg(a.idx + R);
-        grow = static_cast<long long>(b) * a.N + pi;
-        const float* p = a.xyz + grow * 3;
-        const float* c = a.new_xyz + jg * 3;
-        // pointnet2_utils.py:345-348: grouped_xyz -= new_xyz; grouped_xyz /= radius  (fp32 divide)
-        rx = __fdiv_rn(__ldg(p) - __ldg(c), a.radius_div);
-        ry = __fdiv_rn(__ldg(p + 1) - __ldg(c + 1), a.radius_div);
-        rz = __fdiv_rn(__ldg(p + 2) - __ldg(c + 2), a.radius_div);
+    for (int d = 0; d < (CD > 0 ? CD : 1); ++d) fd[d] = in_f[d];
+    if (MMA1) {
+      // ---------------- layer 1 on the tensor cores: thread = row builds its split-bf16 operand ----
+      float v[3 + CD];
+      v[0] = rx; v[1] = ry; v[2] = rz;
 #pragma unroll
-        for (int d = 0; d < CD; ++d) fd[d] = __ldg(a.feat + (static_cast<size_t>(b) * CD + d) * a.N + pi);
+      for (int d = 0; d < CD; ++d) v[3 + d] = fd[d];
+      uint32_t e[K0];  // bf16 bit patterns of the row: [h, m, h, l, h, m] per input, 1, 1, 1, zeros
+#pragma unroll
+      for (int k = 0; k < K0; ++k) e[k] = 0u;
+#pragma unroll
+      for (int d = 0; d < 3 + CD; ++d) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v[d]);
+        const float r1 = v[d] - __bfloat162float(h);
+        const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+        e[6 * d] = e[6 * d + 2] = e[6 * d + 4] = __bfloat16_as_ushort(h);
+        e[6 * d + 1] = e[6 * d + 5] = __bfloat16_as_ushort(m);
+        e[6 * d + 3] = __bfloat16_as_ushort(l);
       }
+      e[NT - 3] = e[NT - 2] = e[NT - 1] = 0x3F80u;  // 1.0
+#pragma unroll
+      for (int ck = 0; ck < K0 / 8; ++ck) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_x + tc::swz_off(tid, ck)),
+                     "r"(e[8 * ck] | (e[8 * ck + 1] << 16)), "r"(e[8 * ck + 2] | (e[8 * ck + 3] << 16)),
+                     "r"(e[8 * ck + 4] | (e[8 * ck + 5] << 16)), "r"(e[8 * ck + 6] | (e[8 * ck + 7] << 16))
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      tc::fence_before_sync();
+      group_sync();
+      if (!weights_ready) {
+        if (!mbar_wait(&bar_w, 0)) { failed = true; break; }
+        weights_ready = true;
+      }
+      if (tid == 0) {
+        tc::fence_after_sync();
+#pragma unroll
+        for (int kk = 0; kk < K0 / 16; ++kk)
+          tc::mma_bf16(tmem_d, tc::smem_desc_sw128(s_x + kk * 32), tc::smem_desc_sw128(s_w1 + kk * 32), idesc1,
+                       kk > 0 ? 1u : 0u);
+        tc::mma_commit(&bar_mma);
+      }
+      if (!mbar_wait(&bar_mma, phase)) { failed = true; break; }
+      phase ^= 1;
+      tc::fence_after_sync();
+      // epilogue 1: thread = row; ReLU folded into the bf16 conversion; X1 overwrites the operand rows
+      const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll
+      for (int c0 = 0; c0 < C1; c0 += 16) {
+        float t[16];
+        tc::tmem_ld16(lane_base + c0, t);
+        const uint32_t chunk = c0 >> 3;
+        const uint32_t pa = s_x + (chunk >> 3) * (128u * 128u);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa + tc::swz_off(tid, chunk & 7u)),
+                     "r"(tc::pack_bf16_relu(t[0], t[1])), "r"(tc::pack_bf16_relu(t[2], t[3])),
+                     "r"(tc::pack_bf16_relu(t[4], t[5])), "r"(tc::pack_bf16_relu(t[6], t[7]))
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa + tc::swz_off(tid, (chunk + 1) & 7u)),
+                     "r"(tc::pack_bf16_relu(t[8], t[9])), "r"(tc::pack_bf16_relu(t[10], t[11])),
+                     "r"(tc::pack_bf16_relu(t[12], t[13])), "r"(tc::pack_bf16_relu(t[14], t[15]))
+                     : "memory");
+      }
+    } else {
+      // ---------------- layer 1: build X1 (bf16) for rows warp*32 .. warp*32+31 -------------------
       // rows in batches of GB: in gather mode the batch's g rows are all requested before the first is
       // used (the loop is bound by that latency: 4 loads in flight per warp left the kernel stalled
       // on `v += g` for a third of its samples)
@@ -178,18 +306,17 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
 #pragma unroll
             for (int q = 0; q < CPL; ++q) v[q] += gq[CD == 0 ? u : 0][q];
           }
-#pragma unroll
-          for (int q = 0; q < CPL; ++q) v[q] = rok ? fmaxf(v[q], 0.f) : 0.f;
           const uint32_t row = warp * 32 + i;
           const uint32_t c0 = lane * CPL;              // first channel of this lane
           const uint32_t chunk = c0 >> 3;               // 16-byte chunk along K
           const uint32_t addr = s_x + (chunk >> 3) * (128u * 128u) + tc::swz_off(row, chunk & 7u) + (c0 & 7u) * 2u;
+          // ReLU folded into the conversion; rows past the end of the batch are stored as zeros
           if (CPL == 4) {
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(tc::pack_bf16(v[0], v[1])),
-                         "r"(tc::pack_bf16(v[2], v[3]))
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(rok ? tc::pack_bf16_relu(v[0], v[1]) : 0u),
+                         "r"(rok ? tc::pack_bf16_relu(v[2], v[3]) : 0u)
                          : "memory");
           } else {
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(tc::pack_bf16(v[0], v[1])) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(rok ? tc::pack_bf16_relu(v[0], v[1]) : 0u) : "memory");
           }
         }
       }
@@ -222,16 +349,16 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
         float v[16];
         tc::tmem_ld16(lane_base + c0, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + s_b2[c0 + i], 0.f);
+        for (int i = 0; i < 16; ++i) v[i] += s_b2[c0 + i];  // the ReLU rides on the bf16 conversion
         const uint32_t chunk = c0 >> 3;
         const uint32_t pa = s_x + (chunk >> 3) * (128u * 128u);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa + tc::swz_off(tid, chunk & 7u)),
-                     "r"(tc::pack_bf16(v[0], v[1])), "r"(tc::pack_bf16(v[2], v[3])), "r"(tc::pack_bf16(v[4], v[5])),
-                     "r"(tc::pack_bf16(v[6], v[7]))
+                     "r"(tc::pack_bf16_relu(v[0], v[1])), "r"(tc::pack_bf16_relu(v[2], v[3])),
+                     "r"(tc::pack_bf16_relu(v[4], v[5])), "r"(tc::pack_bf16_relu(v[6], v[7]))
                      : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa + tc::swz_off(tid, (chunk + 1) & 7u)),
-                     "r"(tc::pack_bf16(v[8], v[9])), "r"(tc::pack_bf16(v[10], v[11])),
-                     "r"(tc::pack_bf16(v[12], v[13])), "r"(tc::pack_bf16(v[14], v[15]))
+                     "r"(tc::pack_bf16_relu(v[8], v[9])), "r"(tc::pack_bf16_relu(v[10], v[11])),
+                     "r"(tc::pack_bf16_relu(v[12], v[13])), "r"(tc::pack_bf16_relu(v[14], v[15]))
                      : "memory");
       }
     }
@@ -255,6 +382,10 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
                        tc::smem_desc_sw128(s_x + po * (128u * 128u) + ko), idesc3, kk > 0 ? 1u : 0u);
         }
         tc::mma_commit(&bar_mma);
+      }
+      if (h == 0) {  // next tile's inputs travel under this tile's epilogue
+        next_tile = s_next[grp][(it + 1) & 1];
+        fetch_row(next_tile);
       }
       if (!mbar_wait(&bar_mma, phase)) { failed = true; break; }
       phase ^= 1;
@@ -285,27 +416,89 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     tc::fence_before_sync();  // ordered before the next tile's __syncthreads / MMA into the same TMEM
   }
   if (failed && tid == 0) atomicExch(a.err, 2);
+  // a group that found no tile never waited for the weights: the bulk copies must have landed before
+  // this CTA's shared memory can be handed to another CTA
+  if (!weights_ready && threadIdx.x == 0) mbar_wait(&bar_w, 0);
   tc::fence_before_sync();
   __syncthreads();
+  // the last CTA to finish re-arms the counter pair for the next launch that uses this slot (no memset
+  // node per launch: with a dozen graphs in flight those serialise on the copy engine)
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.tile_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+      a.tile_counter[0] = 0;
+      a.tile_counter[1] = 0;
+      __threadfence();
+    }
+  }
   if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, tmem_cols);
 }
 
 template <int CPL, int NG>
 int launch_cd(int cd, const SaArgs& a, int grid, size_t smem, cudaStream_t s) {
-#define PN2_SA_CASE(CDV)                                                                                   \
-  case CDV: {                                                                                              \
-    PN2_CUDA(cudaFuncSetAttribute(sa_fused_kernel<CPL, CDV, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+#define PN2_SA_LAUNCH(CDV, M1)                                                                             \
+  {                                                                                                        \
+    PN2_CUDA(cudaFuncSetAttribute(sa_fused_kernel<CPL, CDV, NG, M1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   static_cast<int>(smem)));                                                \
-    sa_fused_kernel<CPL, CDV, NG><<<grid, SA_THREADS * NG, smem, s>>>(a);                                  \
-    break;                                                                                                 \
+    sa_fused_kernel<CPL, CDV, NG, M1><<<grid, SA_THREADS * NG, smem, s>>>(a);                              \
   }
-  switch (cd) {
-    PN2_SA_CASE(0) PN2_SA_CASE(1) PN2_SA_CASE(2) PN2_SA_CASE(3) PN2_SA_CASE(4)
-    default: set_error("sa_group_mlp: direct feature channels must be <= 4 (got %d)", cd); return PN2_ERR_INVALID;
+  if (a.g != nullptr) {  // per-point layer-1 rows are gathered: FMA build (cd == 0, checked by the caller)
+    PN2_SA_LAUNCH(0, false)
+  } else {               // raw channels: layer 1 on the tensor cores
+    switch (cd) {
+      case 0: PN2_SA_LAUNCH(0, true) break;
+      case 1: PN2_SA_LAUNCH(1, true) break;
+      case 2: PN2_SA_LAUNCH(2, true) break;
+      case 3: PN2_SA_LAUNCH(3, true) break;
+      case 4: PN2_SA_LAUNCH(4, true) break;
+      default: set_error("sa_group_mlp: direct feature channels must be <= 4 (got %d)", cd); return PN2_ERR_INVALID;
+    }
   }
-#undef PN2_SA_CASE
+#undef PN2_SA_LAUNCH
   PN2_CHECK_LAUNCH("sa_fused_kernel");
   return PN2_OK;
+}
+
+// One zeroed {next tile, finished CTAs} pair per launch.  Eager launches rotate through a per-device ring
+// (4096 launches would have to be in flight to collide).  A launch that is being captured into a CUDA
+// graph gets a slot of its own that is never handed out again: the graph replays with that address
+// for as long as it lives, possibly concurrently with eager work and with other graphs.
+constexpr int kCounterSlots = 4096;
+constexpr int kCaptureSlots = 1 << 16;  // captured launches per device over the life of the process
+int* g_counters[64] = {nullptr};
+unsigned g_counter_next = 0;
+int* g_capture_chunk[64] = {nullptr};
+int g_capture_used[64] = {0};
+int g_capture_lock = 0;
+
+int* next_tile_counter(cudaStream_t stream) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) return nullptr;
+  if (cap != cudaStreamCaptureStatusNone) {
+    // the chunk was allocated by an earlier eager call (GraphedBackbone warms up before it captures);
+    // allocating here would be an illegal call inside a global-mode capture
+    while (__atomic_exchange_n(&g_capture_lock, 1, __ATOMIC_ACQUIRE)) {}
+    int* slot = nullptr;
+    if (g_capture_chunk[dev] && g_capture_used[dev] < kCaptureSlots) slot = g_capture_chunk[dev] + 2 * g_capture_used[dev]++;
+    __atomic_store_n(&g_capture_lock, 0, __ATOMIC_RELEASE);
+    return slot;
+  }
+  if (!__atomic_load_n(&g_counters[dev], __ATOMIC_ACQUIRE)) {
+    int* p = nullptr;
+    const size_t bytes = 2 * static_cast<size_t>(kCounterSlots + kCaptureSlots) * sizeof(int);
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaFree(p); return nullptr; }  // kernels re-arm their slot
+    int* expected = nullptr;
+    if (!__atomic_compare_exchange_n(&g_counters[dev], &expected, p, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
+      cudaFree(p);
+    } else {
+      g_capture_chunk[dev] = p + 2 * kCounterSlots;
+    }
+  }
+  const unsigned slot = __atomic_fetch_add(&g_counter_next, 1u, __ATOMIC_RELAXED) % kCounterSlots;
+  return g_counters[dev] + 2 * slot;
 }
 
 }  // namespace
@@ -340,7 +533,11 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
   a.total_rows = static_cast<long long>(b) * npoint * nsample;
   a.err = device_err_flag();
   PN2_REQUIRE(a.err != nullptr, "sa_group_mlp: cannot allocate the device error flag");
-  const size_t w_bytes = static_cast<size_t>(c2) * c1 * 2 + static_cast<size_t>(c3) * c2 * 2;
+  a.tile_counter = next_tile_counter(as_stream(stream));
+  PN2_REQUIRE(a.tile_counter != nullptr,
+              "sa_group_mlp: no tile counter (run the op once eagerly before capturing it into a CUDA graph)");
+  const size_t w_bytes = static_cast<size_t>(c2) * c1 * 2 + static_cast<size_t>(c3) * c2 * 2 +
+                         (g == nullptr ? static_cast<size_t>(c1) * 128 : 0);  // + the layer-1 operand panel
   const size_t x_bytes = 128 * static_cast<size_t>(c1 > c2 ? c1 : c2) * 2;
   const long long tiles = (a.total_rows + 127) / 128;
   // Groups per CTA: as many independent 128-thread groups (own tile, own 128 TMEM columns) as shared

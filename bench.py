@@ -51,7 +51,18 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def wait_ready(self, timeout=8.0):
+        """Block until nvidia-smi has delivered its first sample: its start-up takes driver locks that
+        stall kernel launches for tens of milliseconds, which must not land inside the timed region."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        """Samples from here on belong to the timed region."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -77,7 +88,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in self.rows[self.first:] or self.rows[-1:]:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
             except Exception:
@@ -311,10 +322,12 @@ def main():
             main_stream.wait_stream(st)
 
     # ---------------- device-resident throughput --------------------------------------------------
-    run_steps(0, args.warmup, lambda g, s: g(dev_pool[s % POOL]))
-    barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
+    clocks.wait_ready()
+    run_steps(0, args.warmup, lambda g, s: g(dev_pool[s % POOL]))
+    barrier()
+    clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     run_steps(args.warmup, args.steps, lambda g, s: g(dev_pool[s % POOL]))
