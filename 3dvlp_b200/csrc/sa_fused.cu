@@ -46,7 +46,7 @@ struct SaArgs {
   __nv_bfloat16* out_pm; // (B*npoint, C3) bf16 or nullptr
   int* err;
   int* tile_counter;     // {next tile, finished CTAs}, both zero at launch: tiles are handed out dynamically
-  int B, N, npoint, ns, C1, C2, C3;
+  int B, N, npoint, ns, ns_shift, C1, C2, C3;  // ns = 1 << ns_shift
   float radius_div;      // divisor applied to the recentred xyz (radius, or 1 when not normalised)
   long long total_rows;  // B * npoint * ns
 };
@@ -171,12 +171,12 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
 #pragma unroll
     for (int d = 0; d < (CD > 0 ? CD : 1); ++d) in_f[d] = 0.f;
     if (in_ok) {
-      const long long jg = R / ns;  // global centre index b*npoint + j
-      const int b = static_cast<int>(jg / a.npoint);
+      const int jg = static_cast<int>(R >> a.ns_shift);  // global centre index b*npoint + j (< 2^31, host-checked)
+      const int b = jg / a.npoint;
       const int pi = __ldg(a.idx + R);
       in_grow = static_cast<long long>(b) * a.N + pi;  // row of g / point id within the batch-flattened cloud
       const float* p = a.xyz + in_grow * 3;
-      const float* c = a.new_xyz + jg * 3;
+      const float* c = a.new_xyz + static_cast<long long>(jg) * 3;
 #pragma unroll
       for (int d = 0; d < 3; ++d) { in_p[d] = __ldg(p + d); in_c[d] = __ldg(c + d); }
 #pragma unroll
@@ -392,9 +392,13 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
       tc::fence_after_sync();
       // ---- epilogue 3: thread = channel; max over each centre's ns columns ----------------------
       const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
-      const int groups = 128 / ns;
+      const int groups = 128 >> a.ns_shift;
       const int ch = h * 128 + tid;
       const float bias = s_b3[ch];
+      // centres of a tile are consecutive: one 32-bit division per tile, then count up with carry
+      const int jg0 = static_cast<int>(r0 >> a.ns_shift);
+      const int n_centres = a.B * a.npoint;
+      int cb = jg0 / a.npoint, cj = jg0 - cb * a.npoint;
       for (int gidx = 0; gidx < groups; ++gidx) {
         float mx = -INFINITY;
         for (int c0 = 0; c0 < ns; c0 += 16) {
@@ -403,13 +407,13 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
 #pragma unroll
           for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
         }
-        const long long jg = r0 / ns + gidx;  // global centre index
-        if (jg * ns < a.total_rows) {
+        const int jg = jg0 + gidx;  // global centre index
+        if (jg < n_centres) {
           const float o = fmaxf(mx + bias, 0.f);
-          const long long b = jg / a.npoint, j = jg - b * a.npoint;
-          a.out_cm[(b * C3 + ch) * a.npoint + j] = o;
-          if (a.out_pm) a.out_pm[jg * C3 + ch] = __float2bfloat16_rn(o);
+          a.out_cm[(static_cast<long long>(cb) * C3 + ch) * a.npoint + cj] = o;
+          if (a.out_pm) a.out_pm[static_cast<long long>(jg) * C3 + ch] = __float2bfloat16_rn(o);
         }
+        if (++cj == a.npoint) { cj = 0; ++cb; }
       }
     }
     if (failed) break;
@@ -530,6 +534,8 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
   a.out_cm = out_cm; a.out_pm = static_cast<__nv_bfloat16*>(out_pm_bf16);
   a.B = b; a.N = n; a.npoint = npoint; a.ns = nsample; a.C1 = c1; a.C2 = c2; a.C3 = c3;
   a.radius_div = radius_div;
+  a.ns_shift = nsample == 16 ? 4 : (nsample == 32 ? 5 : (nsample == 64 ? 6 : 7));
+  PN2_REQUIRE(static_cast<long long>(b) * npoint < (1LL << 31), "sa_group_mlp: b * npoint must stay below 2^31");
   a.total_rows = static_cast<long long>(b) * npoint * nsample;
   a.err = device_err_flag();
   PN2_REQUIRE(a.err != nullptr, "sa_group_mlp: cannot allocate the device error flag");

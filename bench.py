@@ -45,59 +45,86 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML
+    (nvidia_ml_py).  Spawning `nvidia-smi -lms` instead was measured to stall CUDA-graph launches for
+    milliseconds at a time (its start-up and every poll take driver-wide locks): an intermittent 2x
+    loss on a step that is one graph launch per 0.45 ms.  Falls back to one nvidia-smi query after the
+    region if NVML is unavailable."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_S = 0.025
 
     def __init__(self, index):
-        self.index, self.rows, self.proc, self.first = index, [], None, 0
+        self.index, self.rows, self.first, self.t, self.nv, self.h = index, [], 0, None, None, None
+        self.running = False
 
-    def wait_ready(self, timeout=8.0):
-        """Block until nvidia-smi has delivered its first sample: its start-up takes driver locks that
-        stall kernel launches for tens of milliseconds, which must not land inside the timed region."""
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.running = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while self.running:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((mhz, mask))
+            except Exception:
+                pass
+            time.sleep(self.PERIOD_S)
+
+    def wait_ready(self, timeout=5.0):
         t0 = time.time()
-        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
-            time.sleep(0.02)
+        while self.nv is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
 
     def mark(self):
         """Samples from here on belong to the timed region."""
         self.first = len(self.rows)
 
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.nv is None:
+            return self._one_shot()
+        time.sleep(self.PERIOD_S * 1.5)
+        self.running = False
+        self.t.join(timeout=1.0)
+        rows = self.rows[self.first:] or self.rows[-1:]
+        nv = self.nv
+        names = (("hw_slowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                 ("hw_thermal_slowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                 ("sw_thermal_slowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                 ("sw_power_cap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))
+        reasons = sorted({n for _, mask in rows for n, bit in names if mask & bit})
+        sm = [r[0] for r in rows]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": "nvml"}
+
+    def _one_shot(self):
         try:
-            self.proc.wait(timeout=2)
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+            r = [c.strip() for c in out.split(",")]
+            reasons = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6])
+                       if v.lower().startswith("active")]
+            return {"sm_mhz": float(r[0]), "sm_max_mhz": float(r[1]), "reasons": reasons, "samples": 1,
+                    "source": "nvidia-smi after the region (NVML unavailable)"}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows[self.first:] or self.rows[-1:]:
-            try:
-                sm.append(float(r[0])); mx = float(r[1])
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
 
 
 def build_pool(torch, syn, dev, rank):
@@ -325,6 +352,19 @@ def main():
     clocks = ClockSampler(local_rank)
     clocks.start()
     clocks.wait_ready()
+    # Untimed settling before the W warm-up steps: the first few hundred graph launches of a process are
+    # occasionally issued at ~1 ms each (driver-side first-use work; measured with
+    # tools/throughput_stability.py), which W = 3..24 steps do not cover.  Chunks of 100 steps until two
+    # consecutive chunks agree within 10 %, at most 20 chunks.
+    prev = None
+    for chunk in range(20):
+        t0 = time.perf_counter()
+        run_steps(0, 100, lambda g, s: g(dev_pool[s % POOL]))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if chunk >= 2 and prev is not None and abs(dt - prev) <= 0.1 * prev:
+            break
+        prev = dt
     run_steps(0, args.warmup, lambda g, s: g(dev_pool[s % POOL]))
     barrier()
     clocks.mark()
