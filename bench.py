@@ -172,8 +172,9 @@ def cpu_reference_arm(args, torch, pkg, syn):
             "unit": "scenes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Pointnet2Backbone fwd, %d scenes/GPU x %d pts, C_in=%d" % (SCENES_PER_GPU, N_POINTS, C_IN),
-                       "sample": sample},
+            "config": {"workload": "Pointnet2Backbone fwd, %d scenes/GPU x %d pts, C_in=%d, eval" % (
+                           SCENES_PER_GPU, N_POINTS, C_IN), "scenes_per_gpu": SCENES_PER_GPU, "points": N_POINTS,
+                       "c_in": C_IN, "sample": sample},
             "cpu_baseline": {"value": v, "unit": "scenes/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -281,7 +282,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=24)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=12, help="batches in flight (graph replays on separate streams)")
+    ap.add_argument("--depth", type=int, default=16, help="batches in flight (graph replays on separate streams)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
