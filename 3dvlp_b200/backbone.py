@@ -61,5 +61,5 @@ class Pointnet2Backbone(nn.Module):
         data_dict["fp2_xyz"] = data_dict["sa2_xyz"]
         # seed indices into the input cloud: SA2's FPS over SA1's output starts with SA1's own order
         # (backbone_module.py:108,134)
-        data_dict["fp2_inds"] = data_dict["sa1_inds"][:, : data_dict["fp2_xyz"].shape[1]]
+        data_dict["fp2_inds"] = data_dict["sa1_inds"][:, : data_dict["fp2_xyz"].shape[1]].contiguous()
         return data_dict

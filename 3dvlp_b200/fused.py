@@ -223,7 +223,10 @@ def backbone_forward(bb, data_dict):
     data_dict["fp2_features"] = feats
     data_dict["fp2_xyz"] = data_dict["sa2_xyz"]
     num_seed = data_dict["fp2_xyz"].shape[1]
-    data_dict["fp2_inds"] = data_dict["sa1_inds"][:, 0:num_seed]
+    # same values as the reference's view sa1_inds[:, :num_seed] (backbone_module.py:134), materialised:
+    # a strided device->host copy of this tensor costs the serving loop 0.1 ms per step, a contiguous
+    # one nothing (tools/e2e_probe.py)
+    data_dict["fp2_inds"] = data_dict["sa1_inds"][:, 0:num_seed].contiguous()
     return data_dict
 
 

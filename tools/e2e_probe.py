@@ -21,23 +21,52 @@ d = graphs[0](devp[0])
 out_host = [{k: torch.empty(d[k].shape, dtype=d[k].dtype).pin_memory() for k in outs} for _ in range(depth)]
 
 
+copy_lanes = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+done = [torch.cuda.Event() for _ in range(depth)]
+import time
+
+
 def run(count, mode):
     for st in lanes:
         st.wait_stream(main)
+    t0 = time.perf_counter()
     for s in range(count):
         k = s % depth
         with torch.cuda.stream(lanes[k]):
+            if mode == "side" and s >= depth:
+                lanes[k].wait_event(done[k])   # the previous outputs of this lane have left
             r = graphs[k](host[s % 8] if mode in ("full", "noout") else devp[s % 8])
             if mode in ("full", "noin"):
                 for key in outs:
                     out_host[k][key].copy_(r[key], non_blocking=True)
-    for st in lanes:
+            elif mode == "one":      # a single output copy (features only)
+                out_host[k]["fp2_features"].copy_(r["fp2_features"], non_blocking=True)
+            elif mode == "small":    # only the two small outputs
+                out_host[k]["fp2_xyz"].copy_(r["fp2_xyz"], non_blocking=True)
+                out_host[k]["fp2_inds"].copy_(r["fp2_inds"], non_blocking=True)
+            elif mode == "xyz":
+                out_host[k]["fp2_xyz"].copy_(r["fp2_xyz"], non_blocking=True)
+            elif mode == "inds":
+                out_host[k]["fp2_inds"].copy_(r["fp2_inds"], non_blocking=True)
+            elif mode == "indsc":
+                out_host[k]["fp2_inds"].copy_(r["sa2_inds"], non_blocking=True)   # contiguous tensor of the same size
+            elif mode == "side":     # outputs leave on a per-lane copy stream
+                ev = torch.cuda.Event(); ev.record()
+                with torch.cuda.stream(copy_lanes[k]):
+                    copy_lanes[k].wait_event(ev)
+                    for key in outs:
+                        out_host[k][key].copy_(r[key], non_blocking=True)
+                    done[k].record()
+    global cpu_ms
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / count
+    for st in lanes + copy_lanes:
         main.wait_stream(st)
 
 
-for mode in ("none", "noout", "noin", "full", "none", "full"):
+print("fp2_inds contiguous:", d["fp2_inds"].is_contiguous(), "fp2_xyz:", d["fp2_xyz"].is_contiguous())
+for mode in ("none", "xyz", "inds", "indsc", "small", "full"):
     run(200, mode); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(steps, mode); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    print("%-6s %.4f ms/step  %.0f scenes/s" % (mode, ms, 8e3 / ms), flush=True)
+    print("%-6s %.4f ms/step  %.0f scenes/s   cpu issue %.4f ms/step" % (mode, ms, 8e3 / ms, cpu_ms), flush=True)
