@@ -42,7 +42,7 @@ def stream_of(t):
 
 
 # Kernel launches issued per C-ABI call (for bench.py's `gpu_launches` claim and per-op timing).
-KERNELS_PER_CALL = {"pn2_nn_distance": 2, "pn2_nn_distance_grad": 2}  # (pn2_ball_query on a large cloud launches 4; counted as 1)
+KERNELS_PER_CALL = {"pn2_nn_distance": 2, "pn2_nn_distance_grad": 2, "pn2_sa_group_mlp": 4}  # (pn2_ball_query on a large cloud launches 4; counted as 1)
 launch_count = 0
 profile = None  # when a list: every call appends (name, tag, start_event, end_event)
 profile_tag = ""

@@ -29,6 +29,7 @@ namespace pn2 {
 namespace {
 
 constexpr int SA_THREADS = 128;
+constexpr int kMaxScenes = 64;  // scenes per launch
 
 struct SaArgs {
   const float* xyz;      // (B, N, 3)
@@ -43,9 +44,11 @@ struct SaArgs {
   const uint8_t* w3p;    // packed (C3, C2)
   const float* b3;
   float* out_cm;         // (B, C3, npoint) fp32
-  __nv_bfloat16* out_pm; // (B*npoint, C3) bf16 or nullptr
   int* err;
   int* tile_counter;     // {next tile, finished CTAs}, both zero at launch: tiles are handed out dynamically
+  const int* row_src;    // (B, cap) compacted rows: index into idx (centre * ns + slot) or -1; see sa_plan_kernel
+  const int* tiles_b;    // (B) tiles of each scene's compacted row list
+  int cap;               // row capacity of a scene's region: npoint * ns rounded up to 128
   int B, N, npoint, ns, ns_shift, C1, C2, C3;  // ns = 1 << ns_shift
   float radius_div;      // divisor applied to the recentred xyz (radius, or 1 when not normalised)
   long long total_rows;  // B * npoint * ns
@@ -70,7 +73,9 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   __shared__ __align__(8) uint64_t bar_w, bar_mma_g[NG];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_next[NG][2];  // next tile of each group, double-buffered by iteration parity
-  __shared__ float s_b2[128], s_b3[256];
+  __shared__ uint32_t s_end[NG][2][4];    // bit r: row r of the group's tile is the last row of its centre in this tile
+  __shared__ int s_tpre[kMaxScenes + 1];  // prefix sums of tiles_b: tile id -> scene
+  __shared__ float s_b2[128];
 
   constexpr int C1 = 32 * CPL;
   const int grp = threadIdx.x / SA_THREADS;            // group of this thread
@@ -94,7 +99,6 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     fence_mbar_init_cluster();
   }
   for (int i = threadIdx.x; i < C2; i += SA_THREADS * NG) s_b2[i] = a.b2[i];
-  for (int i = threadIdx.x; i < C3; i += SA_THREADS * NG) s_b3[i] = a.b3[i];
   if (MMA1) {
     // B operand of layer 1: row = channel, K-major: [w_h, w_h, w_m, w_h, w_l, w_m] per input (against
     // [v_h, v_m, v_h, v_l, v_h, v_m]), [b_h, b_m, b_l] against ones, zeros up to K0
@@ -124,6 +128,11 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   // (several batches in flight) part of the grid starts late, and a late CTA must find the work
   // already done instead of a full static share of it.
   if (tid == 0) s_next[grp][0] = atomicAdd(a.tile_counter, 1);
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < a.B; ++b) { s_tpre[b] = acc; acc += __ldg(a.tiles_b + b); }
+    s_tpre[a.B] = acc;
+  }
   if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot, tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
@@ -152,28 +161,41 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   const uint32_t idesc1 = tc::idesc_bf16_f32(128, C1);
   const uint32_t idesc2 = tc::idesc_bf16_f32(128, C2);
   const uint32_t idesc3 = tc::idesc_bf16_f32(128, 128);
-  const long long n_tiles = (a.total_rows + 127) / 128;
+  const long long n_tiles = s_tpre[a.B];  // tiles of the compacted row lists of all scenes
   uint32_t phase = 0;
   bool weights_ready = false, failed = false;
 
-  // Inputs of this thread's row (row = tile * 128 + tid): neighbour index -> point coordinates, centre,
-  // raw channels.  A dependent chain of two global round trips, so the NEXT tile's inputs are requested
-  // while the current tile is still in its layer-3 epilogue.
+  // Inputs of this thread's row: compacted row -> (centre, slot) -> neighbour index -> point coordinates,
+  // centre, raw channels.  A dependent chain of global round trips, so the NEXT tile's inputs are
+  // requested while the current tile is still in its layer-3 epilogue.
   float in_p[3], in_c[3], in_f[CD > 0 ? CD : 1];
   long long in_grow = 0;
   bool in_ok = false;
-  auto fetch_row = [&](long long t) {
-    const long long R = t * 128 + tid;
-    in_ok = t < n_tiles && R < a.total_rows;
+  int in_scene = 0;
+  const int* in_rs = a.row_src;  // compacted rows of the tile
+  auto fetch_row = [&](long long t, int par) {
+    in_ok = false;
     in_grow = 0;
 #pragma unroll
     for (int d = 0; d < 3; ++d) in_p[d] = in_c[d] = 0.f;
 #pragma unroll
     for (int d = 0; d < (CD > 0 ? CD : 1); ++d) in_f[d] = 0.f;
+    if (t >= n_tiles) return;  // uniform over the group
+    int b = 0;
+    while (s_tpre[b + 1] <= t) ++b;  // scene of the tile (few scenes: linear search)
+    in_scene = b;
+    const int* rs = a.row_src + static_cast<long long>(b) * a.cap + (t - s_tpre[b]) * 128;
+    in_rs = rs;
+    const int src = __ldg(rs + tid);
+    const int nxt = tid < 127 ? __ldg(rs + tid + 1) : -1;
+    const int jg = src >= 0 ? (src >> a.ns_shift) : -1;  // global centre index b*npoint + j (< 2^31, host-checked)
+    // a centre may continue in the next tile: each tile flushes its part with an atomic max
+    const bool last = src >= 0 && (nxt < 0 || (nxt >> a.ns_shift) != jg);
+    const uint32_t m = __ballot_sync(0xffffffffu, last);
+    if (lane == 0) s_end[grp][par][warp] = m;
+    in_ok = src >= 0;
     if (in_ok) {
-      const int jg = static_cast<int>(R >> a.ns_shift);  // global centre index b*npoint + j (< 2^31, host-checked)
-      const int b = jg / a.npoint;
-      const int pi = __ldg(a.idx + R);
+      const int pi = __ldg(a.idx + src);
       in_grow = static_cast<long long>(b) * a.N + pi;  // row of g / point id within the batch-flattened cloud
       const float* p = a.xyz + in_grow * 3;
       const float* c = a.new_xyz + static_cast<long long>(jg) * 3;
@@ -184,10 +206,11 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     }
   };
   long long tile = s_next[grp][0], next_tile = n_tiles;
-  fetch_row(tile);
+  fetch_row(tile, 0);
 
   for (int it = 0; tile < n_tiles && !failed; ++it, tile = next_tile) {
-    const long long r0 = tile * 128;
+    const int scene = in_scene;  // of THIS tile (fetch_row for the next one overwrites these)
+    const int* rs_tile = in_rs;
     // claim the tile after this one; the group reads it after the next group_sync (the other parity
     // slot was last read an iteration ago, several group_syncs back)
     if (tid == 0) s_next[grp][(it + 1) & 1] = atomicAdd(a.tile_counter, 1);
@@ -385,35 +408,46 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
       }
       if (h == 0) {  // next tile's inputs travel under this tile's epilogue
         next_tile = s_next[grp][(it + 1) & 1];
-        fetch_row(next_tile);
+        fetch_row(next_tile, (it + 1) & 1);
       }
+      // centre of column lane + 32 q (warp-uniform at flush time: fetched by shuffle), requested before the wait
+      int cid[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cid[q] = __ldg(rs_tile + lane + 32 * q);
       if (!mbar_wait(&bar_mma, phase)) { failed = true; break; }
       phase ^= 1;
       tc::fence_after_sync();
-      // ---- epilogue 3: thread = channel; max over each centre's ns columns ----------------------
+      // ---- epilogue 3: thread = channel; running max over the columns, flushed where a centre ends ----
       const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
-      const int groups = 128 >> a.ns_shift;
+      // The rows of a centre are consecutive TMEM columns; the end mask is the same for every thread, so
+      // the flush branch never diverges.  A centre that continues in another tile is completed by that
+      // tile's flush: outputs are ReLU'd (>= 0), out_cm starts at zero, and an integer max on the bit
+      // patterns of non-negative floats is the float max.
       const int ch = h * 128 + tid;
-      const float bias = s_b3[ch];
-      // centres of a tile are consecutive: one 32-bit division per tile, then count up with carry
-      const int jg0 = static_cast<int>(r0 >> a.ns_shift);
-      const int n_centres = a.B * a.npoint;
-      int cb = jg0 / a.npoint, cj = jg0 - cb * a.npoint;
-      for (int gidx = 0; gidx < groups; ++gidx) {
-        float mx = -INFINITY;
-        for (int c0 = 0; c0 < ns; c0 += 16) {
-          float v[16];
-          tc::tmem_ld16(lane_base + gidx * ns + c0, v);
+      const float bias = __ldg(a.b3 + ch);
+      const int par = it & 1;
+      uint32_t endm[4];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+      for (int w = 0; w < 4; ++w) endm[w] = s_end[grp][par][w];
+      const int last_col = endm[3] ? 127 - __clz(endm[3]) : (endm[2] ? 95 - __clz(endm[2])
+                         : (endm[1] ? 63 - __clz(endm[1]) : (endm[0] ? 31 - __clz(endm[0]) : -1)));
+      int* out_bits = reinterpret_cast<int*>(a.out_cm) + (static_cast<long long>(scene) * C3 + ch) * a.npoint -
+                      static_cast<long long>(scene) * a.npoint;  // + global centre index
+      float mx = -INFINITY;
+      for (int c0 = 0; c0 <= last_col; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(lane_base + c0, v);
+        const uint32_t bits = (endm[c0 >> 5] >> (c0 & 31)) & 0xffffu;
+        const int cidq = (c0 & 64) ? ((c0 & 32) ? cid[3] : cid[2]) : ((c0 & 32) ? cid[1] : cid[0]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          mx = fmaxf(mx, v[i]);
+          if (bits & (1u << i)) {
+            const int jg = __shfl_sync(0xffffffffu, cidq, (c0 + i) & 31) >> a.ns_shift;
+            asm volatile("red.global.max.s32 [%0], %1;" ::"l"(out_bits + jg), "r"(__float_as_int(fmaxf(mx + bias, 0.f))) : "memory");
+            mx = -INFINITY;
+          }
         }
-        const int jg = jg0 + gidx;  // global centre index
-        if (jg < n_centres) {
-          const float o = fmaxf(mx + bias, 0.f);
-          a.out_cm[(static_cast<long long>(cb) * C3 + ch) * a.npoint + cj] = o;
-          if (a.out_pm) a.out_pm[static_cast<long long>(jg) * C3 + ch] = __float2bfloat16_rn(o);
-        }
-        if (++cj == a.npoint) { cj = 0; ++cb; }
       }
     }
     if (failed) break;
@@ -436,6 +470,93 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     }
   }
   if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Row plan.  ball_query pads every ball to nsample entries by repeating its first hit
+// (ball_query_gpu.cu:40-44); a repeated row has the inputs of slot 0, so its activations are a copy of
+// slot 0's and the max-pool cannot see it.  On ScanNet-density scenes balls hold 28 of 64 (SA1) and 7
+// of 32 (SA2) distinct points on average.  sa_count_kernel counts each centre's distinct hits (the
+// first repeat of idx[0] ends them: points are unique); one CTA per scene then takes the exclusive
+// prefix sum and writes, per
+// compacted row, the index of its entry in idx (-1 for the tail of the last tile); the fused kernel then
+// runs ceil(sum / 128) tiles per scene instead of npoint * nsample / 128, with bit-identical output.
+// The counting kernel also zero-fills out_cm (the fused kernel combines with an atomic max).
+// ---------------------------------------------------------------------------------------------
+// distinct hits of every centre (warp per centre, all scenes at once) + zero-fill of out_cm
+__global__ void __launch_bounds__(256)
+sa_count_kernel(int n_centres, int ns, const int* __restrict__ idx, int* __restrict__ cnt_out,
+                float4* __restrict__ out4, long long n_out4) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n_out4; i += static_cast<long long>(gridDim.x) * 256)
+    out4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j >= n_centres) return;
+  const int* row = idx + static_cast<long long>(j) * ns;
+  const int first = __ldg(row);
+  int v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = lane + 32 * k < ns ? __ldg(row + lane + 32 * k) : -2;  // ns <= 128
+  int cnt = ns;
+#pragma unroll
+  for (int k = 3; k >= 0; --k) {
+    const int sl = lane + 32 * k;
+    const uint32_t m = __ballot_sync(0xffffffffu, sl > 0 && sl < ns && v[k] == first);
+    if (m) cnt = 32 * k + __ffs(m) - 1;  // descending k: the lowest repeat wins
+  }
+  if (lane == 0) cnt_out[j] = cnt;
+}
+
+// per scene: exclusive scan of the counts, then one warp per centre writes its compacted rows
+__global__ void __launch_bounds__(1024)
+sa_plan_kernel(int npoint, int ns_shift, int cap, const int* __restrict__ cnt_in, int* __restrict__ row_src,
+               int* __restrict__ tiles_b) {
+  extern __shared__ int s_plan[];  // off[npoint + 1], then 33 words of scan scratch
+  int* s_off = s_plan;
+  int* s_scan = s_plan + npoint + 1;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int* cntb = cnt_in + static_cast<long long>(b) * npoint;
+  const int per = (npoint + blockDim.x - 1) / blockDim.x;  // <= 4 (npoint <= 4096)
+  const int j0 = threadIdx.x * per;
+  int mine[4], local = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { mine[q] = (q < per && j0 + q < npoint) ? __ldg(cntb + j0 + q) : 0; local += mine[q]; }
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nwarps ? s_scan[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += o;
+    }
+    s_scan[lane] = w;  // inclusive over warps
+    if (lane == 31) s_scan[32] = w;
+  }
+  __syncthreads();
+  int run = incl - local + (warp > 0 ? s_scan[warp - 1] : 0);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (q < per && j0 + q < npoint) { s_off[j0 + q] = run; run += mine[q]; }
+  }
+  const int total = s_scan[32];
+  if (threadIdx.x == 0) { s_off[npoint] = total; tiles_b[b] = (total + 127) >> 7; }
+  __syncthreads();
+  int* dst = row_src + static_cast<long long>(b) * cap;
+  for (int j = warp; j < npoint; j += nwarps) {
+    const int off = s_off[j], c = s_off[j + 1] - off;
+    const int base = (b * npoint + j) << ns_shift;
+    for (int sl = lane; sl < c; sl += 32) dst[off + sl] = base + sl;
+  }
+  const int padded = (total + 127) & ~127;
+  for (int i = total + threadIdx.x; i < padded; i += blockDim.x) dst[i] = -1;
 }
 
 template <int CPL, int NG>
@@ -531,7 +652,7 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
   SaArgs a;
   a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx; a.g = g; a.feat = feat; a.w1 = w1; a.b1 = b1;
   a.w2p = static_cast<const uint8_t*>(w2_packed); a.b2 = b2; a.w3p = static_cast<const uint8_t*>(w3_packed); a.b3 = b3;
-  a.out_cm = out_cm; a.out_pm = static_cast<__nv_bfloat16*>(out_pm_bf16);
+  a.out_cm = out_cm;
   a.B = b; a.N = n; a.npoint = npoint; a.ns = nsample; a.C1 = c1; a.C2 = c2; a.C3 = c3;
   a.radius_div = radius_div;
   a.ns_shift = nsample == 16 ? 4 : (nsample == 32 ? 5 : (nsample == 64 ? 6 : 7));
@@ -542,6 +663,40 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
   a.tile_counter = next_tile_counter(as_stream(stream));
   PN2_REQUIRE(a.tile_counter != nullptr,
               "sa_group_mlp: no tile counter (run the op once eagerly before capturing it into a CUDA graph)");
+  // ---- row plan (stream-ordered workspace: the call stays asynchronous and capturable) -----------------
+  PN2_REQUIRE(b <= kMaxScenes, "sa_group_mlp: at most %d scenes per call (got %d)", kMaxScenes, b);
+  PN2_REQUIRE(npoint <= 4096, "sa_group_mlp: npoint=%d exceeds the row plan's 4096", npoint);
+  PN2_REQUIRE(static_cast<long long>(b) * npoint * nsample < (1LL << 31), "sa_group_mlp: b * npoint * nsample must stay below 2^31");
+  const int cap = (npoint * nsample + 127) & ~127;
+  const size_t plan_smem = (static_cast<size_t>(npoint) + 40) * sizeof(int);
+  {  // keep freed workspace in the stream-ordered pool instead of returning it to the OS at every sync
+    static bool pool_ready[64] = {false};
+    int dev = 0;
+    PN2_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_ready[dev] = true;
+    }
+  }
+  int* ws = nullptr;
+  const size_t n_centres = static_cast<size_t>(b) * npoint;
+  PN2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (static_cast<size_t>(b) * cap + b + n_centres) * sizeof(int),
+                           as_stream(stream)));
+  int* tiles_b = ws + static_cast<size_t>(b) * cap;
+  int* cnt_ws = tiles_b + b;
+  a.row_src = ws; a.tiles_b = tiles_b; a.cap = cap;
+  {
+    const long long n_out4 = (static_cast<long long>(b) * c3 * npoint) >> 2;  // c3 is a multiple of 128
+    sa_count_kernel<<<static_cast<unsigned>((n_centres + 7) / 8), 256, 0, as_stream(stream)>>>(
+        static_cast<int>(n_centres), nsample, idx, cnt_ws, reinterpret_cast<float4*>(out_cm), n_out4);
+    sa_plan_kernel<<<b, 1024, plan_smem, as_stream(stream)>>>(npoint, a.ns_shift, cap, cnt_ws, ws, tiles_b);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFreeAsync(ws, as_stream(stream)); return cuda_fail(e, "sa_plan_kernel"); }
+  }
   const size_t w_bytes = static_cast<size_t>(c2) * c1 * 2 + static_cast<size_t>(c3) * c2 * 2 +
                          (g == nullptr ? static_cast<size_t>(c1) * 128 : 0);  // + the layer-1 operand panel
   const size_t x_bytes = 128 * static_cast<size_t>(c1 > c2 ? c1 : c2) * 2;
@@ -563,14 +718,19 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
   long long grid = static_cast<long long>(sm_count()) * resident;
   if (grid * ng > tiles) grid = (tiles + ng - 1) / ng;
   cudaStream_t s = as_stream(stream);
+  int rc;
   if (ng == 4) {
-    if (c1 == 128) return launch_cd<4, 4>(c_direct, a, static_cast<int>(grid), smem, s);
-    return launch_cd<2, 4>(c_direct, a, static_cast<int>(grid), smem, s);
+    rc = c1 == 128 ? launch_cd<4, 4>(c_direct, a, static_cast<int>(grid), smem, s)
+                   : launch_cd<2, 4>(c_direct, a, static_cast<int>(grid), smem, s);
+  } else if (ng == 2) {
+    rc = c1 == 128 ? launch_cd<4, 2>(c_direct, a, static_cast<int>(grid), smem, s)
+                   : launch_cd<2, 2>(c_direct, a, static_cast<int>(grid), smem, s);
+  } else {
+    rc = c1 == 128 ? launch_cd<4, 1>(c_direct, a, static_cast<int>(grid), smem, s)
+                   : launch_cd<2, 1>(c_direct, a, static_cast<int>(grid), smem, s);
   }
-  if (ng == 2) {
-    if (c1 == 128) return launch_cd<4, 2>(c_direct, a, static_cast<int>(grid), smem, s);
-    return launch_cd<2, 2>(c_direct, a, static_cast<int>(grid), smem, s);
-  }
-  if (c1 == 128) return launch_cd<4, 1>(c_direct, a, static_cast<int>(grid), smem, s);
-  return launch_cd<2, 1>(c_direct, a, static_cast<int>(grid), smem, s);
+  cudaFreeAsync(ws, s);
+  // the bf16 point-major twin (next layer's GEMM operand) is a transpose of the finished out_cm
+  if (rc == PN2_OK && out_pm_bf16) rc = pn2_pack_rows_bf16(b, c3, npoint, c3, out_cm, out_pm_bf16, stream);
+  return rc;
 }

@@ -195,9 +195,14 @@ int pn2_linear_bf16(int m, int n, int k, const void* x_bf16, const void* w_packe
  *   to 4 raw channels evaluated in fp32; `g` (b*n, c1) fp32, if non-NULL, is the per-point
  *   contribution W1[:,3:] . features precomputed with pn2_linear_bf16 (wide inputs);
  *   w2_packed (c2,c1), w3_packed (c3,c2) from pn2_pack_weight_bf16; b1/b2/b3 fp32 folded biases;
- *   c1,c2 in {64,128}, c3 in {128,256}, nsample in {16,32,64,128}.
- * Outputs: out_cm (b,c3,npoint) fp32 -- the reference's feature layout -- and, if non-NULL,
- * out_pm_bf16 (b*npoint, c3) bf16 point-major rows ready to be the next layer's GEMM operand. */
+ *   c1,c2 in {64,128}, c3 in {128,256}, nsample in {16,32,64,128}, b <= 64, npoint <= 4096.
+ *   idx must follow pn2_ball_query's padding contract (slots past the last distinct hit repeat
+ *   idx[..,0]; ball_query_gpu.cu:40-44): the repeated rows are recognised and not recomputed --
+ *   their activations equal slot 0's, so the max-pool is unchanged.
+ * Outputs: out_cm (b,c3,npoint) fp32 -- the reference's feature layout, zero-filled by the call --
+ * and, if non-NULL, out_pm_bf16 (b*npoint, c3) bf16 point-major rows ready to be the next layer's
+ * GEMM operand.  Launches four kernels (count, row plan, fused body, bf16 transpose) and takes its
+ * workspace from the stream-ordered allocator: asynchronous, re-entrant, capturable. */
 int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float radius_div, const float* xyz,
                      const float* new_xyz, const int* idx, int c_direct, const float* feat,
                      const float* g, int c1, int c2, int c3, const float* w1, const float* b1,

@@ -61,6 +61,11 @@ SA_CASES = {
     "sa3_like": (3, 1024, 256, 250, 0.8, 16, [128, 128, 256]),
     "voteagg_like": (2, 1024, 256, 256, 0.3, 16, [128, 128, 128]),
     "wide_input": (1, 2500, 132, 200, 0.3, 64, [64, 64, 128]),
+    # the fused kernel skips ball-query padding rows: nearly empty balls (1-3 distinct hits, hundreds of
+    # centres per tile), completely full balls (no row to skip) and a ragged tail (centres straddle tiles)
+    "sparse_balls": (2, 3000, 1, 300, 0.03, 64, [64, 64, 128]),
+    "full_balls": (2, 1200, 1, 130, 5.0, 32, [64, 64, 128]),
+    "sparse_balls_wide": (2, 2048, 128, 517, 0.05, 32, [128, 128, 256]),
 }
 
 
