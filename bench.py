@@ -282,7 +282,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=24)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=16, help="batches in flight (graph replays on separate streams)")
+    ap.add_argument("--depth", type=int, default=20, help="batches in flight (graph replays on separate streams)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
