@@ -56,6 +56,10 @@ def _version_key(module):
     return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
 
 
+MAX_NPOINT = 4096   # limits of pn2_sa_group_mlp's row plan (include/pointnet2_b200.h)
+MAX_SCENES = 64
+
+
 class _SaPlan:
     def __init__(self, module):
         blocks = list(module.mlp_module.children())
@@ -78,6 +82,8 @@ class _SaPlan:
     @staticmethod
     def supported(module):
         if not (module.use_xyz and module.pooling == "max" and module.nsample in _NS_OK):
+            return False
+        if module.npoint is None or module.npoint > MAX_NPOINT:  # row plan of pn2_sa_group_mlp
             return False
         if not _plain_relu_mlp(module.mlp_module, 3):
             return False
@@ -143,7 +149,7 @@ def sa_forward(module, xyz, features, inds):
     if plan is None:
         return None
     c_feat = 0 if features is None else features.shape[1]
-    if c_feat != plan.c_in or xyz.dtype != torch.float32:
+    if c_feat != plan.c_in or xyz.dtype != torch.float32 or xyz.shape[0] > MAX_SCENES:
         return None
     xyz = xyz.contiguous()
     inds, new_xyz = sa_sample(module, xyz, inds)
@@ -173,7 +179,7 @@ def backbone_forward(bb, data_dict):
             return None
         plans.append(plan)
     pc = data_dict["point_clouds"]
-    if pc.dtype != torch.float32 or pc.size(-1) - 3 != plans[0].c_in:
+    if pc.dtype != torch.float32 or pc.size(-1) - 3 != plans[0].c_in or pc.shape[0] > MAX_SCENES:
         return None
     rows1 = None
     if plans[0].direct or plans[0].c_in == 0:

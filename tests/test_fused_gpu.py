@@ -189,3 +189,21 @@ def test_graphed_backbone_replays_identically(pkg, cuda):
             want = bb({"point_clouds": pc.clone()})
         for k, v in got.items():
             assert torch.equal(v, want[k]), k
+
+
+def test_sa_module_beyond_fused_limits_takes_generic_path(pkg, cuda):
+    """More than 64 scenes per call (the fused kernel's row-plan limit) silently uses the op-by-op path:
+    same indices, features within the mixed-precision tolerance of the fused result on the two halves."""
+    from common import cloud, fill_state_dict
+    pc = cloud(77, 70, 600, c_extra=1, extent=1.0)
+    xyz = pc[..., :3].contiguous().to(cuda)
+    feats = pc[..., 3:].transpose(1, 2).contiguous().to(cuda)
+    m = pkg.PointnetSAModuleVotes(npoint=64, radius=0.3, nsample=16, mlp=[1, 64, 64, 128], use_xyz=True, normalize_xyz=True)
+    fill_state_dict(m)
+    m = m.to(cuda).eval()
+    with torch.no_grad():
+        nx, nf, ii = m(xyz, feats)
+        halves = [m(xyz[s].contiguous(), feats[s].contiguous()) for s in (slice(0, 35), slice(35, 70))]
+    assert torch.equal(ii, torch.cat([h[2] for h in halves])) and torch.equal(nx, torch.cat([h[0] for h in halves]))
+    want = torch.cat([h[1] for h in halves])
+    assert (nf - want).abs().max().item() / want.abs().max().item() < 3e-2
