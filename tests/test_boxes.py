@@ -278,3 +278,71 @@ def test_contrast_module_equals_reference_loops(pkg, cuda, OB):
     assert m.pc_proj.weight.grad is not None and m.text_proj.weight.grad is not None
     early = m(to_dev(grounding_inputs(21, epoch=3), cuda))       # constrast_module.py:54-56
     assert float(early["con_loss"]) == 0.0 and "lang_con_loss" not in early
+
+
+def _nccl_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        C = importlib.import_module("3dvlp_b200.contrast")
+        dev = torch.device("cuda", rank)
+        torch.manual_seed(0)
+        m = C.ContrastModule(CONFIG).to(dev)                        # same weights on every rank
+        datas = [grounding_inputs(60 + r, B=2, epoch=60) for r in range(world)]
+        out = m(to_dev(datas[rank], dev), gather=True)
+        local = m(to_dev(datas[rank], dev), gather=False)
+        # expected sentence term: this rank's sentences against the kept objects of every rank
+        import torch.nn.functional as F
+        BU = importlib.import_module("3dvlp_b200.box_util")
+        LG = importlib.import_module("3dvlp_b200.loss_grounding")
+        boxes, objs = [], []
+        for d in datas:
+            dd = to_dev(d, dev)
+            boxes.append(F.normalize(m.pc_proj(dd["bbox_feature"]), dim=-1))
+            objs.append(dd["objectness_scores"].max(2)[1].bool())
+        all_box, all_obj = torch.cat(boxes).reshape(-1, 128), torch.cat(objs).reshape(-1)
+        dd = to_dev(datas[rank], dev)
+        gc, gs = LG.gt_boxes_from_labels(dd, CONFIG)
+        ious, _ = BU.box3d_diou_pairs(dd["pred_center"], dd["pred_size"], gc, gs + 1e-2)
+        obj = objs[rank]
+        target = ((ious > 0.25) & obj[:, None]).float()
+        B, K = obj.shape
+        Lmax = gc.shape[1]
+        text = F.normalize(m.text_proj(dd["lang_emb"].view(B, Lmax, -1)), dim=-1)
+        want = 0.
+        for b in range(B):
+            for j in range(int(dd["lang_num"][b])):
+                logp = torch.log_softmax(text[b, j] @ all_box[all_obj].t(), -1)
+                tgt = torch.zeros(all_obj.numel(), device=dev)
+                tgt[(rank * B + b) * K:(rank * B + b + 1) * K] = target[b, j]
+                want = want + (-(logp * tgt[all_obj]).sum() / obj[b].sum() / 2)
+        torch.testing.assert_close(out["lang_con_loss"], want / B, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(out["iou_con_loss"], local["iou_con_loss"])
+        out["lang_con_loss"].backward()
+        assert m.pc_proj.weight.grad is not None
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_contrast_all_gather_world2_nccl(cuda):
+    """The north star's one collective over NCCL/NVLink: needs two GPUs (skipped on a one-GPU box)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 2000
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
