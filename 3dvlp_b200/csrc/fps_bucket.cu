@@ -236,11 +236,16 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs 
   // ================= init: temps, bucket records, bucket and group boxes ==========================
   for (int b = warp; b < nb; b += FB_WARPS)
     process_bucket(b, 0u, true, sorted[b * FB_BK + lane], sorted[b * FB_BK + 32 + lane]);
-  // thread = bucket (tid < nb), warp = group of 32 consecutive buckets
+  // thread = bucket, warp = group of GB consecutive buckets.  GB = ceil(nb / 32) spreads the buckets over
+  // all 32 warps: every warp reports a candidate to the acceptance step (32 instead of nb / 32), and the
+  // bound -- the best value no group reported -- comes from smaller groups, so more samples are
+  // accepted per round.
+  const int GB = (nb + FB_WARPS - 1) / FB_WARPS;
+  const int myb = (lane < GB && warp * GB + lane < nb) ? warp * GB + lane : -1;
   Box bbox = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
-  if (tid < nb) {
+  if (myb >= 0) {
     for (int i = 0; i < FB_BK; ++i) {
-      const float4 p = sorted[tid * FB_BK + i];
+      const float4 p = sorted[myb * FB_BK + i];
       if (__float_as_int(p.w) >= 0) {
         bbox.lx = fminf(bbox.lx, p.x); bbox.ly = fminf(bbox.ly, p.y); bbox.lz = fminf(bbox.lz, p.z);
         bbox.hx = fmaxf(bbox.hx, p.x); bbox.hy = fmaxf(bbox.hy, p.y); bbox.hz = fmaxf(bbox.hz, p.z);
@@ -262,9 +267,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs 
     if (oxyz) { oxyz[0] = x0; oxyz[1] = y0; oxyz[2] = z0; }
   }
   __syncthreads();
-  float bmax = tid < nb ? bb_a[tid].x : -1.f;
+  float bmax = myb >= 0 ? bb_a[myb].x : -1.f;
   float gmax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(bmax)));
-  const bool has_group = warp * 32 < nb;  // warp-uniform
+  const bool has_group = warp * GB < nb;  // warp-uniform
 
 #ifdef PN2_FB_DEBUG
   long long dbg_items = 0, dbg_t[5] = {0, 0, 0, 0, 0}, dbg_prev = clock64();
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs 
       uint32_t gmask = __ballot_sync(0xffffffffu, gaff);
       if (gmask != 0u) {
         uint32_t mask = 0u;
-        const bool live = tid < nb && bmax >= 0.f;
+        const bool live = myb >= 0 && bmax >= 0.f;
         while (gmask) {
           const int c = __ffs(gmask) - 1;
           gmask &= gmask - 1;
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs 
           int base = 0;
           if (lane == 0) base = atomicAdd(&nwork, __popc(any));
           base = __shfl_sync(0xffffffffu, base, 0);
-          if (mask) work[base + __popc(any & lt)] = static_cast<uint32_t>(tid) | (mask << 16);
+          if (mask) work[base + __popc(any & lt)] = static_cast<uint32_t>(myb) | (mask << 16);
         }
       }
     }
@@ -336,9 +341,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs 
       uint32_t bkey = 0xffffffffu;
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
       float rz = 0.f;
-      if (tid < nb) {
-        r = bb_a[tid];
-        const float2 q = bb_b[tid];
+      if (myb >= 0) {
+        r = bb_a[myb];
+        const float2 q = bb_b[myb];
         best = __float_as_int(r.x); bkey = __float_as_uint(r.y);
         second = __float_as_int(q.y); rz = q.x;
       }
