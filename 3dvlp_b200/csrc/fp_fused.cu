@@ -34,7 +34,7 @@ __device__ __forceinline__ void insert3(float d, int i, float& b1, float& b2, fl
 __global__ void __launch_bounds__(FP_THREADS)
 fp_prepare_kernel(int n, int m, int c1, int c2, int kpad, const float* __restrict__ unknown,
                   const float* __restrict__ known, const float* __restrict__ uf, const float* __restrict__ kf,
-                  __nv_bfloat16* __restrict__ out) {
+                  const int* __restrict__ pre_idx, const float* __restrict__ pre_w, __nv_bfloat16* __restrict__ out) {
   __shared__ float4 sk[FP_KTILE];
   __shared__ float s_b[4][32][3];
   __shared__ int s_i[4][32][3];
@@ -48,50 +48,60 @@ fp_prepare_kernel(int n, int m, int c1, int c2, int kpad, const float* __restric
   const float* kfb = kf + static_cast<size_t>(scene) * c2 * m;
   const float* ufb = uf ? uf + static_cast<size_t>(scene) * c1 * n : nullptr;
 
-  // ---- three nearest known points + weights for the CTA's 32 unknown points --------------------
-  // lane = unknown point; the four warps each scan a quarter of every staged tile of known points
-  // and warp 0 merges the four sorted triples by (distance, index).
   const int j = p0 + lane;
-  float ux = 0.f, uy = 0.f, uz = 0.f;
-  if (j < n) { ux = __ldg(unknown + 3 * j); uy = __ldg(unknown + 3 * j + 1); uz = __ldg(unknown + 3 * j + 2); }
-  float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
-  int i1 = 0, i2 = 0, i3 = 0;
-  for (int t0 = 0; t0 < m; t0 += FP_KTILE) {
-    const int tn = min(FP_KTILE, m - t0);
-    __syncthreads();
-    for (int q = tid; q < tn; q += FP_THREADS)
-      sk[q] = make_float4(__ldg(known + 3 * (t0 + q)), __ldg(known + 3 * (t0 + q) + 1), __ldg(known + 3 * (t0 + q) + 2), 0.f);
-    __syncthreads();
-    const int quarter = (tn + 3) >> 2;
-    const int k_end = min(tn, (warp + 1) * quarter);
-    for (int k = warp * quarter; k < k_end; ++k) {
-      const float4 p = sk[k];
-      const float d = sqdist3(ux - p.x, uy - p.y, uz - p.z);
-      if (d < b3) {  // b1 <= b2 <= b3 always: one compare rejects almost every candidate
-        if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = t0 + k; }
-        else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = t0 + k; }
-        else { b3 = d; i3 = t0 + k; }
+  int a1, a2, a3;
+  float w1, w2, w3;
+  if (pre_idx != nullptr) {
+    // neighbours and weights were computed ahead of time (pn2_three_nn_weights: they depend on the
+    // coordinates only, so the backbone evaluates them on its sampling stream, off the critical path)
+    const size_t o = (static_cast<size_t>(scene) * n + (j < n ? j : 0)) * 3;
+    a1 = __ldg(pre_idx + o); a2 = __ldg(pre_idx + o + 1); a3 = __ldg(pre_idx + o + 2);
+    w1 = __ldg(pre_w + o); w2 = __ldg(pre_w + o + 1); w3 = __ldg(pre_w + o + 2);
+  } else {
+    // ---- three nearest known points + weights for the CTA's 32 unknown points --------------------
+    // lane = unknown point; the four warps each scan a quarter of every staged tile of known points
+    // and warp 0 merges the four sorted triples by (distance, index).
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (j < n) { ux = __ldg(unknown + 3 * j); uy = __ldg(unknown + 3 * j + 1); uz = __ldg(unknown + 3 * j + 2); }
+    float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+    int i1 = 0, i2 = 0, i3 = 0;
+    for (int t0 = 0; t0 < m; t0 += FP_KTILE) {
+      const int tn = min(FP_KTILE, m - t0);
+      __syncthreads();
+      for (int q = tid; q < tn; q += FP_THREADS)
+        sk[q] = make_float4(__ldg(known + 3 * (t0 + q)), __ldg(known + 3 * (t0 + q) + 1), __ldg(known + 3 * (t0 + q) + 2), 0.f);
+      __syncthreads();
+      const int quarter = (tn + 3) >> 2;
+      const int k_end = min(tn, (warp + 1) * quarter);
+      for (int k = warp * quarter; k < k_end; ++k) {
+        const float4 p = sk[k];
+        const float d = sqdist3(ux - p.x, uy - p.y, uz - p.z);
+        if (d < b3) {  // b1 <= b2 <= b3 always: one compare rejects almost every candidate
+          if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = t0 + k; }
+          else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = t0 + k; }
+          else { b3 = d; i3 = t0 + k; }
+        }
       }
     }
+    s_b[warp][lane][0] = b1; s_b[warp][lane][1] = b2; s_b[warp][lane][2] = b3;
+    s_i[warp][lane][0] = i1; s_i[warp][lane][1] = i2; s_i[warp][lane][2] = i3;
+    __syncthreads();
+    if (warp == 0) {
+  #pragma unroll
+      for (int w = 1; w < 4; ++w)
+  #pragma unroll
+        for (int t = 0; t < 3; ++t) insert3(s_b[w][lane][t], s_i[w][lane][t], b1, b2, b3, i1, i2, i3);
+      // pointnet2_utils.py:138-140 (sqrt) and pointnet2_modules.py:395-397 (1/(d+1e-8), normalise)
+      const float r1 = __fdiv_rn(1.0f, __fsqrt_rn(b1) + 1e-8f), r2 = __fdiv_rn(1.0f, __fsqrt_rn(b2) + 1e-8f),
+                  r3 = __fdiv_rn(1.0f, __fsqrt_rn(b3) + 1e-8f);
+      const float norm = (r1 + r2) + r3;
+      s_idx[lane][0] = i1; s_idx[lane][1] = i2; s_idx[lane][2] = i3;
+      s_w[lane][0] = __fdiv_rn(r1, norm); s_w[lane][1] = __fdiv_rn(r2, norm); s_w[lane][2] = __fdiv_rn(r3, norm);
+    }
+    __syncthreads();
+    a1 = s_idx[lane][0]; a2 = s_idx[lane][1]; a3 = s_idx[lane][2];
+    w1 = s_w[lane][0]; w2 = s_w[lane][1]; w3 = s_w[lane][2];
   }
-  s_b[warp][lane][0] = b1; s_b[warp][lane][1] = b2; s_b[warp][lane][2] = b3;
-  s_i[warp][lane][0] = i1; s_i[warp][lane][1] = i2; s_i[warp][lane][2] = i3;
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int w = 1; w < 4; ++w)
-#pragma unroll
-      for (int t = 0; t < 3; ++t) insert3(s_b[w][lane][t], s_i[w][lane][t], b1, b2, b3, i1, i2, i3);
-    // pointnet2_utils.py:138-140 (sqrt) and pointnet2_modules.py:395-397 (1/(d+1e-8), normalise)
-    const float r1 = __fdiv_rn(1.0f, __fsqrt_rn(b1) + 1e-8f), r2 = __fdiv_rn(1.0f, __fsqrt_rn(b2) + 1e-8f),
-                r3 = __fdiv_rn(1.0f, __fsqrt_rn(b3) + 1e-8f);
-    const float norm = (r1 + r2) + r3;
-    s_idx[lane][0] = i1; s_idx[lane][1] = i2; s_idx[lane][2] = i3;
-    s_w[lane][0] = __fdiv_rn(r1, norm); s_w[lane][1] = __fdiv_rn(r2, norm); s_w[lane][2] = __fdiv_rn(r3, norm);
-  }
-  __syncthreads();
-  const int a1 = s_idx[lane][0], a2 = s_idx[lane][1], a3 = s_idx[lane][2];
-  const float w1 = s_w[lane][0], w2 = s_w[lane][1], w3 = s_w[lane][2];
   const bool live = j < n;
 
   // ---- 64 channels per pass: lane = point, warp = 16-channel slice; transpose; store ----------
@@ -127,6 +137,56 @@ fp_prepare_kernel(int n, int m, int c1, int c2, int kpad, const float* __restric
   }
 }
 
+
+// Three nearest known points of every unknown point and their normalised inverse-distance weights,
+// one WARP per unknown point: each lane keeps the best three of its stride of the known set with the
+// reference's strict-`<` cascade (interpolate_gpu.cu:39-55), then three rounds of a warp-wide
+// lexicographic (distance, index) minimum pop the global best three -- the order the serial cascade
+// over ascending indices produces.  Weights as pointnet2_utils.py:138-140 + pointnet2_modules.py:395-397.
+__global__ void __launch_bounds__(256)
+three_nn_weights_kernel(int n, int m, const float* __restrict__ unknown, const float* __restrict__ known,
+                        int* __restrict__ idx, float* __restrict__ weight) {
+  const int lane = threadIdx.x & 31, scene = blockIdx.y;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= n) return;
+  const float* u = unknown + (static_cast<size_t>(scene) * n + j) * 3;
+  const float* kn = known + static_cast<size_t>(scene) * m * 3;
+  const float ux = __ldg(u), uy = __ldg(u + 1), uz = __ldg(u + 2);
+  float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int k = lane; k < m; k += 32) {
+    const float d = sqdist3(ux - __ldg(kn + 3 * k), uy - __ldg(kn + 3 * k + 1), uz - __ldg(kn + 3 * k + 2));
+    if (d < b3) {
+      if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
+      else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
+      else { b3 = d; i3 = k; }
+    }
+  }
+  float rd[3];
+  int ri[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    // distances are >= 0 (or +inf for an empty slot): their bit patterns order like the floats
+    const uint32_t dbits = __float_as_uint(b1);
+    const uint32_t dmin = __reduce_min_sync(0xffffffffu, dbits);
+    const uint32_t cand = dbits == dmin ? static_cast<uint32_t>(i1) : 0xffffffffu;
+    const uint32_t imin = __reduce_min_sync(0xffffffffu, cand);
+    rd[t] = __uint_as_float(dmin);
+    ri[t] = static_cast<int>(imin);
+    if (dbits == dmin && static_cast<uint32_t>(i1) == imin && dmin != 0x7f800000u) {  // pop the winner's head
+      b1 = b2; i1 = i2; b2 = b3; i2 = i3; b3 = INFINITY; i3 = 0;
+    }
+  }
+  if (lane == 0) {
+    const float r1 = __fdiv_rn(1.0f, __fsqrt_rn(rd[0]) + 1e-8f), r2 = __fdiv_rn(1.0f, __fsqrt_rn(rd[1]) + 1e-8f),
+                r3 = __fdiv_rn(1.0f, __fsqrt_rn(rd[2]) + 1e-8f);
+    const float norm = (r1 + r2) + r3;
+    const size_t o = (static_cast<size_t>(scene) * n + j) * 3;
+    idx[o] = ri[0]; idx[o + 1] = ri[1]; idx[o + 2] = ri[2];
+    weight[o] = __fdiv_rn(r1, norm); weight[o + 1] = __fdiv_rn(r2, norm); weight[o + 2] = __fdiv_rn(r3, norm);
+  }
+}
+
 }  // namespace
 }  // namespace pn2
 
@@ -141,7 +201,33 @@ extern "C" int pn2_fp_prepare(int b, int n, int m, int c1, int c2, int kpad, con
               "fp_prepare: bad arguments");
   dim3 grid((n + 31) / 32, b, (kpad + FP_CH_PER_CTA - 1) / FP_CH_PER_CTA);
   fp_prepare_kernel<<<grid, FP_THREADS, 0, as_stream(stream)>>>(n, m, c1, c2, kpad, unknown, known, unknow_feats,
-                                                               known_feats, static_cast<__nv_bfloat16*>(out_bf16));
+                                                               known_feats, nullptr, nullptr,
+                                                               static_cast<__nv_bfloat16*>(out_bf16));
+  PN2_CHECK_LAUNCH("fp_prepare_kernel");
+  return PN2_OK;
+}
+
+extern "C" int pn2_three_nn_weights(int b, int n, int m, const float* unknown, const float* known, int* idx,
+                                    float* weight, void* stream) {
+  if (b <= 0 || n <= 0) return PN2_OK;
+  PN2_REQUIRE(m > 0 && unknown && known && idx && weight && b <= 65535, "three_nn_weights: bad arguments");
+  dim3 grid((n + 7) / 8, b);
+  three_nn_weights_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, m, unknown, known, idx, weight);
+  PN2_CHECK_LAUNCH("three_nn_weights_kernel");
+  return PN2_OK;
+}
+
+extern "C" int pn2_fp_prepare_indexed(int b, int n, int m, int c1, int c2, int kpad, const int* idx,
+                                      const float* weight, const float* unknow_feats, const float* known_feats,
+                                      void* out_bf16, void* stream) {
+  if (b <= 0 || n <= 0) return PN2_OK;
+  PN2_REQUIRE(m > 0 && c2 > 0 && c1 >= 0 && kpad >= c1 + c2 && kpad % 64 == 0, "fp_prepare_indexed: bad sizes");
+  PN2_REQUIRE(idx && weight && known_feats && out_bf16 && (c1 == 0 || unknow_feats) && b <= 65535,
+              "fp_prepare_indexed: bad arguments");
+  dim3 grid((n + 31) / 32, b, (kpad + FP_CH_PER_CTA - 1) / FP_CH_PER_CTA);
+  fp_prepare_kernel<<<grid, FP_THREADS, 0, as_stream(stream)>>>(n, m, c1, c2, kpad, nullptr, nullptr, unknow_feats,
+                                                               known_feats, idx, weight,
+                                                               static_cast<__nv_bfloat16*>(out_bf16));
   PN2_CHECK_LAUNCH("fp_prepare_kernel");
   return PN2_OK;
 }

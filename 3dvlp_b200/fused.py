@@ -206,6 +206,11 @@ def backbone_forward(bb, data_dict):
             ev.record(side)
             geo.append((inds, new_xyz, ev))
             x = new_xyz
+        # the FP layers' neighbour search needs coordinates only: it runs here, under the SA feature kernels
+        nn1 = fp_neighbours(geo[2][1], geo[3][1])   # fp1: unknown = sa3_xyz, known = sa4_xyz
+        nn2 = fp_neighbours(geo[1][1], geo[2][1])   # fp2: unknown = sa2_xyz, known = sa3_xyz
+        nn_ev = torch.cuda.Event()
+        nn_ev.record(side)
     x, f = xyz, features
     names = ("sa1", "sa2", "sa3", "sa4")
     for name, sa, plan, (inds, new_xyz, ev) in zip(names, sas, plans, geo):
@@ -224,8 +229,16 @@ def backbone_forward(bb, data_dict):
         data_dict[name + "_features"] = f
         if name in ("sa1", "sa2"):
             data_dict[name + "_inds"] = inds
-    feats = bb.fp1(data_dict["sa3_xyz"], data_dict["sa4_xyz"], data_dict["sa3_features"], data_dict["sa4_features"])
-    feats = bb.fp2(data_dict["sa2_xyz"], data_dict["sa3_xyz"], data_dict["sa2_features"], feats)
+    main.wait_event(nn_ev)
+    if not capturing:
+        for t in nn1 + nn2:
+            t.record_stream(main)
+    feats = fp_forward(bb.fp1, data_dict["sa3_xyz"], data_dict["sa4_xyz"], data_dict["sa3_features"],
+                       data_dict["sa4_features"], nn=nn1)
+    if feats is None:
+        feats = bb.fp1(data_dict["sa3_xyz"], data_dict["sa4_xyz"], data_dict["sa3_features"], data_dict["sa4_features"])
+    up = fp_forward(bb.fp2, data_dict["sa2_xyz"], data_dict["sa3_xyz"], data_dict["sa2_features"], feats, nn=nn2)
+    feats = up if up is not None else bb.fp2(data_dict["sa2_xyz"], data_dict["sa3_xyz"], data_dict["sa2_features"], feats)
     data_dict["fp2_features"] = feats
     data_dict["fp2_xyz"] = data_dict["sa2_xyz"]
     num_seed = data_dict["fp2_xyz"].shape[1]
@@ -256,7 +269,17 @@ class _FpPlan:
         return all(o % 64 == 0 for o in outs[:-1])  # a hidden width is the next layer's K
 
 
-def fp_forward(module, unknown, known, unknow_feats, known_feats):
+def fp_neighbours(unknown, known):
+    """(idx (B,n,3) i32, weight (B,n,3) f32) of an FP layer: three_nn + normalised 1/(d+1e-8) weights."""
+    b, n = unknown.shape[0], unknown.shape[1]
+    idx = torch.empty(b, n, 3, device=unknown.device, dtype=torch.int32)
+    w = torch.empty(b, n, 3, device=unknown.device, dtype=torch.float32)
+    L.call("pn2_three_nn_weights", b, n, known.shape[1], L.ptr(unknown.contiguous()), L.ptr(known.contiguous()),
+           L.ptr(idx), L.ptr(w), L.stream_of(unknown), device=unknown.device)
+    return idx, w
+
+
+def fp_forward(module, unknown, known, unknow_feats, known_feats, nn=None):
     """PointnetFPModule.forward (pointnet2_modules.py:371-416) in 1 + n_layers launches: the fused
     three_nn/interpolate/concat front end, then one tcgen05 linear kernel per MLP layer (the last
     one stores straight into the reference's (B, C, n) layout)."""
@@ -278,8 +301,12 @@ def fp_forward(module, unknown, known, unknow_feats, known_feats):
     kpad = plan.layers[0][0].kpad
     x = torch.empty(b * n, kpad, device=dev, dtype=torch.bfloat16)
     uf = unknow_feats.contiguous().float() if unknow_feats is not None else None
-    L.call("pn2_fp_prepare", b, n, m, c1, c2, kpad, L.ptr(unknown.contiguous()), L.ptr(known.contiguous()),
-           L.ptr(uf), L.ptr(known_feats.contiguous().float()), L.ptr(x), L.stream_of(unknown), device=dev)
+    if nn is not None:   # neighbours / weights computed ahead of time (backbone_forward: on the sampling stream)
+        L.call("pn2_fp_prepare_indexed", b, n, m, c1, c2, kpad, L.ptr(nn[0]), L.ptr(nn[1]), L.ptr(uf),
+               L.ptr(known_feats.contiguous().float()), L.ptr(x), L.stream_of(unknown), device=dev)
+    else:
+        L.call("pn2_fp_prepare", b, n, m, c1, c2, kpad, L.ptr(unknown.contiguous()), L.ptr(known.contiguous()),
+               L.ptr(uf), L.ptr(known_feats.contiguous().float()), L.ptr(x), L.stream_of(unknown), device=dev)
     last = len(plan.layers) - 1
     for i, (w, bias) in enumerate(plan.layers):
         if i < last:

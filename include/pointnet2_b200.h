@@ -218,6 +218,18 @@ int pn2_fp_prepare(int b, int n, int m, int c1, int c2, int kpad, const float* u
                    const float* known, const float* unknow_feats, const float* known_feats,
                    void* out_bf16, void* stream);
 
+/* three_nn (interpolate.cpp:19-45) fused with the inverse-distance weights of PointnetFPModule
+ * (pointnet2_utils.py:138-140 sqrt, pointnet2_modules.py:395-397 1/(d+1e-8), normalise):
+ * unknown (b,n,3), known (b,m,3) -> idx (b,n,3) i32, weight (b,n,3) f32.  Same neighbours, order and
+ * ties as pn2_three_nn.  Depends on coordinates only: the backbone runs it on its sampling stream. */
+int pn2_three_nn_weights(int b, int n, int m, const float* unknown, const float* known, int* idx,
+                         float* weight, void* stream);
+
+/* pn2_fp_prepare with the neighbours and weights given (idx, weight from pn2_three_nn_weights). */
+int pn2_fp_prepare_indexed(int b, int n, int m, int c1, int c2, int kpad, const int* idx,
+                           const float* weight, const float* unknow_feats, const float* known_feats,
+                           void* out_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

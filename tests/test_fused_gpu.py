@@ -207,3 +207,23 @@ def test_sa_module_beyond_fused_limits_takes_generic_path(pkg, cuda):
     assert torch.equal(ii, torch.cat([h[2] for h in halves])) and torch.equal(nx, torch.cat([h[0] for h in halves]))
     want = torch.cat([h[1] for h in halves])
     assert (nf - want).abs().max().item() / want.abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("n,m", [(512, 256), (1024, 512), (50, 3), (50, 2), (50, 1), (777, 1500)])
+def test_three_nn_weights_kernel(pkg, oracle, cuda, n, m):
+    """Warp-per-point neighbour search + weights (run ahead of the FP layers on the sampling stream):
+    same neighbours, order and ties as three_nn, weights as PointnetFPModule computes them."""
+    import importlib
+    from common import cloud
+    fused = importlib.import_module("3dvlp_b200.fused")
+    u = cloud(160 + n, 2, n, extent=1.0)[..., :3].contiguous()
+    k = cloud(161 + m, 2, m, extent=1.0)[..., :3].contiguous()
+    if m > 2:
+        k[:, 2] = k[:, 1]            # duplicate known points: equal distances, earlier index wins
+        k[:, 0] = u[:, 5]            # unknown == known: d = 0
+    d2w, iw = oracle.ext.three_nn(u, k)
+    idx, w = fused.fp_neighbours(u.to(cuda), k.to(cuda))
+    assert torch.equal(idx.cpu(), iw)
+    recip = 1.0 / (torch.sqrt(d2w) + 1e-8)      # pointnet2_modules.py:395-397
+    want = recip / recip.sum(dim=2, keepdim=True)
+    torch.testing.assert_close(w.cpu(), want, rtol=2e-6, atol=1e-7)
