@@ -114,14 +114,15 @@ def sa_sample(module, xyz, inds=None):
     return inds, new_xyz
 
 
-def sa_features(module, plan, xyz, features, new_xyz, rows=None):
+def sa_features(module, plan, xyz, features, new_xyz, rows=None, idx=None):
     """Ball query + (wide inputs: per-point GEMM) + the fused grouping/MLP/max-pool kernel.
     `rows`: the (B*N, kpad) bf16 point-major operand of the per-point GEMM when the caller already
     has it (then `features` is not read)."""
     b, n = xyz.shape[0], xyz.shape[1]
     dev = xyz.device
     c_feat = 0 if features is None else features.shape[1]
-    idx = _ext.ball_query(new_xyz, xyz, module.radius, module.nsample)
+    if idx is None:
+        idx = _ext.ball_query(new_xyz, xyz, module.radius, module.nsample)
     g = None
     feat = None
     if plan.direct:
@@ -157,6 +158,7 @@ def sa_forward(module, xyz, features, inds):
 
 
 _side_streams = {}
+_aux_streams = {}
 
 
 def backbone_forward(bb, data_dict):
@@ -195,8 +197,12 @@ def backbone_forward(bb, data_dict):
     side = _side_streams.get(dev)
     if side is None:
         side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    aux = _aux_streams.get(dev)
+    if aux is None:
+        aux = _aux_streams[dev] = torch.cuda.Stream(device=dev)
     capturing = torch.cuda.is_current_stream_capturing()
     side.wait_stream(main)
+    aux.wait_stream(main)
     geo = []
     with torch.cuda.stream(side):
         x = xyz
@@ -211,19 +217,36 @@ def backbone_forward(bb, data_dict):
         nn2 = fp_neighbours(geo[1][1], geo[2][1])   # fp2: unknown = sa2_xyz, known = sa3_xyz
         nn_ev = torch.cuda.Event()
         nn_ev.record(side)
+    # ball queries need coordinates only too, but must not delay the sampling chain: a third stream runs
+    # query i as soon as FPS i is done, next to FPS i+1 and to the feature kernels of layer i-1
+    balls = []
+    with torch.cuda.stream(aux):
+        x = xyz
+        for sa, (inds, new_xyz, ev) in zip(sas, geo):
+            aux.wait_event(ev)
+            if not capturing:
+                new_xyz.record_stream(aux)
+            idx = _ext.ball_query(new_xyz, x, sa.radius, sa.nsample)
+            bev = torch.cuda.Event()
+            bev.record(aux)
+            balls.append((idx, bev))
+            x = new_xyz
     x, f = xyz, features
     names = ("sa1", "sa2", "sa3", "sa4")
-    for name, sa, plan, (inds, new_xyz, ev) in zip(names, sas, plans, geo):
+    for name, sa, plan, (inds, new_xyz, ev), (idx, bev) in zip(names, sas, plans, geo, balls):
         main.wait_event(ev)
+        main.wait_event(bev)
         if not capturing:  # graph-private pool memory is never handed to another stream
             inds.record_stream(main)
             new_xyz.record_stream(main)
+            idx.record_stream(main)
         r = rows1 if name == "sa1" else None
         c_feat = plan.c_in if r is not None else (0 if f is None else f.shape[1])
         if c_feat != plan.c_in:
             main.wait_stream(side)
+            main.wait_stream(aux)
             return None
-        f = sa_features(sa, plan, x, f, new_xyz, rows=r)
+        f = sa_features(sa, plan, x, f, new_xyz, rows=r, idx=idx)
         x = new_xyz
         data_dict[name + "_xyz"] = x
         data_dict[name + "_features"] = f
