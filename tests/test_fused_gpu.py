@@ -66,6 +66,8 @@ SA_CASES = {
     "sparse_balls": (2, 3000, 1, 300, 0.03, 64, [64, 64, 128]),
     "full_balls": (2, 1200, 1, 130, 5.0, 32, [64, 64, 128]),
     "sparse_balls_wide": (2, 2048, 128, 517, 0.05, 32, [128, 128, 256]),
+    "ns128": (1, 900, 1, 37, 0.6, 128, [64, 64, 128]),          # a full ball is exactly one tile
+    "tiny": (1, 40, 0, 3, 0.5, 16, [64, 64, 128]),               # fewer rows than one tile
 }
 
 
