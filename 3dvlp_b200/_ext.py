@@ -27,14 +27,17 @@ def furthest_point_sampling(points, nsamples):
     return out
 
 
-def furthest_point_sampling_gather(points, nsamples):
-    """FPS fused with the gather that follows it in every SA module: returns (inds, new_xyz)."""
+def furthest_point_sampling_gather(points, nsamples, ordered=False):
+    """FPS fused with the gather that follows it in every SA module: returns (inds, new_xyz).
+    ordered=True: the caller believes `points` is the output of a previous FPS (SA2..SA4 of the
+    backbone); the kernel side verifies that and short-cuts -- the result is the same either way."""
     L.check_contiguous(points, "points"); L.check_float(points, "points")
     L.require_cuda_path(points)
     b, n = points.size(0), points.size(1)
     out = torch.zeros(b, nsamples, device=points.device, dtype=torch.int32)
     new_xyz = torch.empty(b, nsamples, 3, device=points.device, dtype=torch.float32)
-    L.call("pn2_furthest_point_sampling_gather", b, n, int(nsamples), L.ptr(points), L.ptr(out),
+    L.call("pn2_furthest_point_sampling_gather_ordered" if ordered else "pn2_furthest_point_sampling_gather",
+           b, n, int(nsamples), L.ptr(points), L.ptr(out),
            L.ptr(new_xyz), L.stream_of(points), device=points.device)
     return out, new_xyz
 

@@ -52,6 +52,7 @@ struct FpsArgs {
   int* idxs;         // (b, m)
   float* new_xyz;    // (b, m, 3) or nullptr
   int* err;          // device error flag (protocol time-out)
+  const int* in_order;  // per scene: 1 = the input is verified to be in FPS order (fps_prefix.cu), or nullptr
   int n, m, log2bs, rows, csize;
   long long* dbg;    // PN2_FPS_TIMING builds only
 };
@@ -109,6 +110,14 @@ __global__ void __launch_bounds__(THREADS, (P <= 5 && THREADS <= 512) ? 2 : 1) f
   int* __restrict__ idxs = a.idxs + static_cast<size_t>(scene) * m;
   float* __restrict__ oxyz = a.new_xyz ? a.new_xyz + static_cast<size_t>(scene) * m * 3 : nullptr;
 
+  if (!CLUSTERED && a.in_order != nullptr && a.in_order[scene] != 0) {
+    // verified on the device: the reference's samples are 0, 1, ..., m-1
+    for (int k = tid; k < m; k += THREADS) {
+      idxs[k] = k;
+      if (oxyz) { oxyz[3 * k] = xyz[3 * k]; oxyz[3 * k + 1] = xyz[3 * k + 1]; oxyz[3 * k + 2] = xyz[3 * k + 2]; }
+    }
+    return;
+  }
   const uint32_t bsmask = (1u << log2bs) - 1u;
   // Thread -> reference-thread map: consecutive reference threads (consecutive point indices) are
   // dealt to DIFFERENT warps, so that when the input is already in sampling order (SA2..SA4 run FPS
@@ -421,7 +430,11 @@ static int run_cfg(int cluster, int threads, FpsArgs a, int bs, int b, cudaStrea
   return dispatch_p<1024, true>(p, a, b, stream, max_active);
 }
 
-int fps_run(int b, int n, int m, const float* dataset, int* idxs, float* new_xyz, cudaStream_t stream) {
+int fps_prefix_check(int b, int n, int m, int log2bs, const float* dataset, void* ws, const int** verdict,
+                     cudaStream_t stream);  // fps_prefix.cu
+
+int fps_run(int b, int n, int m, const float* dataset, int* idxs, float* new_xyz, cudaStream_t stream,
+            bool maybe_in_order = false) {
   if (m <= 0 || b <= 0) return PN2_OK;  // sampling_gpu.cu:78
   PN2_REQUIRE(n > 0, "furthest_point_sampling: n must be positive (got %d)", n);
   PN2_REQUIRE(dataset && idxs, "furthest_point_sampling: null pointer");
@@ -432,6 +445,7 @@ int fps_run(int b, int n, int m, const float* dataset, int* idxs, float* new_xyz
   a.xyz = dataset; a.idxs = idxs; a.new_xyz = new_xyz;
   a.n = n; a.m = m; a.log2bs = log2bs; a.rows = (n + bs - 1) / bs; a.csize = 1;
   a.err = device_err_flag();
+  a.in_order = nullptr;
   a.dbg = nullptr;
 #ifdef PN2_FPS_TIMING
   if (!fps_dbg_ptr) cudaMalloc(&fps_dbg_ptr, 8 * sizeof(long long));
@@ -456,6 +470,16 @@ int fps_run(int b, int n, int m, const float* dataset, int* idxs, float* new_xyz
   } else if (n <= 8192) {
     cluster = 1;
     threads = force_threads ? force_threads : (n <= 2048 ? 512 : 1024);
+    if (maybe_in_order && m >= 2 && m <= n && m <= 8192) {
+      // the caller believes the input is a previous FPS output: verify that in parallel (fps_prefix.cu);
+      // the kernel below then only writes 0..m-1 for the scenes where it holds
+      void* ws = nullptr;
+      PN2_CUDA(cudaMallocAsync(&ws, static_cast<size_t>(b) * m * sizeof(float) + b * sizeof(int), stream));
+      int rc = fps_prefix_check(b, n, m, log2bs, dataset, ws, &a.in_order, stream);
+      if (rc == PN2_OK) rc = run_cfg(cluster, threads, a, bs, b, stream, nullptr);
+      cudaFreeAsync(ws, stream);
+      return rc;
+    }
   } else {
     // The largest cluster whose co-resident count covers the whole batch in ONE wave (a B200 GPC
     // holds a single 16-CTA cluster and one GPC is short of 16 SMs: 7 such clusters fit, 15 of 8).
@@ -498,4 +522,9 @@ extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float* dat
 extern "C" int pn2_furthest_point_sampling_gather(int b, int n, int m, const float* dataset, int* idxs,
                                                   float* new_xyz, void* stream) {
   return pn2::fps_run(b, n, m, dataset, idxs, new_xyz, pn2::as_stream(stream));
+}
+
+extern "C" int pn2_furthest_point_sampling_gather_ordered(int b, int n, int m, const float* dataset, int* idxs,
+                                                          float* new_xyz, void* stream) {
+  return pn2::fps_run(b, n, m, dataset, idxs, new_xyz, pn2::as_stream(stream), true);
 }

@@ -106,10 +106,10 @@ def _sa_plan(module):
     return module._fused
 
 
-def sa_sample(module, xyz, inds=None):
+def sa_sample(module, xyz, inds=None, ordered=False):
     """FPS (+ the xyz gather) of an SA layer -- geometry only, independent of the features."""
     if inds is None:
-        return _ext.furthest_point_sampling_gather(xyz, module.npoint)
+        return _ext.furthest_point_sampling_gather(xyz, module.npoint, ordered=ordered)
     new_xyz = torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
     return inds, new_xyz
 
@@ -206,8 +206,10 @@ def backbone_forward(bb, data_dict):
     geo = []
     with torch.cuda.stream(side):
         x = xyz
-        for sa in sas:
-            inds, new_xyz = sa_sample(sa, x)
+        for li, sa in enumerate(sas):
+            # from the second layer on the input is the previous layer's FPS output: almost surely in
+            # furthest-point order already, which the kernel side verifies instead of recomputing
+            inds, new_xyz = sa_sample(sa, x, ordered=li > 0)
             ev = torch.cuda.Event()
             ev.record(side)
             geo.append((inds, new_xyz, ev))

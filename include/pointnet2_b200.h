@@ -218,6 +218,14 @@ int pn2_fp_prepare(int b, int n, int m, int c1, int c2, int kpad, const float* u
                    const float* known, const float* unknow_feats, const float* known_feats,
                    void* out_bf16, void* stream);
 
+/* pn2_furthest_point_sampling_gather for an input the caller believes to be in furthest-point order
+ * already -- the samples of a previous FPS call, which is what SA2..SA4 of the backbone receive
+ * (backbone_module.py:101-113).  The belief is verified on the device in parallel (n*m distance
+ * tests without the serial chain); where it holds the result 0..m-1 is written directly, elsewhere the
+ * regular kernel runs.  Output identical to pn2_furthest_point_sampling_gather in every case. */
+int pn2_furthest_point_sampling_gather_ordered(int b, int n, int m, const float* dataset, int* idxs,
+                                               float* new_xyz, void* stream);
+
 /* three_nn (interpolate.cpp:19-45) fused with the inverse-distance weights of PointnetFPModule
  * (pointnet2_utils.py:138-140 sqrt, pointnet2_modules.py:395-397 1/(d+1e-8), normalise):
  * unknown (b,n,3), known (b,m,3) -> idx (b,n,3) i32, weight (b,n,3) f32.  Same neighbours, order and

@@ -316,3 +316,43 @@ def test_autograd_ops_backward(pkg, cuda):
     (h2,) = torch.autograd.grad((r3 * wo).sum(), f)
     torch.testing.assert_close(o3, r3, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(h1, h2, rtol=1e-5, atol=1e-5)
+
+
+ORDERED_CASES = ["uniform_5000", "dups_4000", "lattice_1728", "origin_2048", "all_origin_600", "n1000", "n300",
+                 "n2048_to_1024", "cluster_9000", "identical_700"]
+
+
+@pytest.mark.parametrize("name", ORDERED_CASES)
+def test_fps_ordered_hint_never_changes_the_result(pkg, oracle, cuda, name):
+    """pn2_furthest_point_sampling_gather_ordered verifies on the device that its input is already in
+    furthest-point order and short-cuts to 0..m-1; ties (duplicates, lattices), near-origin points and
+    inputs that are NOT in order must all give exactly the reference's samples."""
+    build, _ = FPS_CASES[name]
+    x = build()
+    b, n = x.shape[0], x.shape[1]
+    n_sub = min(n, 2048)
+    order = oracle.ext.furthest_point_sampling(x, n_sub).long()
+    y = torch.gather(x, 1, order.unsqueeze(-1).expand(-1, -1, 3)).contiguous()   # a previous layer's FPS output
+    for pts, tag in ((y, "in order"), (x[:, :n_sub].contiguous(), "raw"), (y.flip(1).contiguous(), "reversed")):
+        for m in sorted({1, 2, max(1, n_sub // 2), max(1, n_sub - 1)}):
+            want = oracle.ext.furthest_point_sampling(pts, m)
+            got, nx = pkg._ext.furthest_point_sampling_gather(pts.to(cuda), m, ordered=True)
+            assert torch.equal(got.cpu(), want), (name, tag, m)
+            assert torch.equal(nx.cpu(), torch.gather(pts, 1, want.long().unsqueeze(-1).expand(-1, -1, 3)))
+    if name == "uniform_5000":   # the shortcut is actually taken on clean data, and per scene
+        want = oracle.ext.furthest_point_sampling(y, n_sub // 2)
+        assert torch.equal(want[0], torch.arange(n_sub // 2, dtype=torch.int32))
+        mixed = torch.cat([y[:1], x[1:, :n_sub]], 0).contiguous()
+        got, _ = pkg._ext.furthest_point_sampling_gather(mixed.to(cuda), 700, ordered=True)
+        assert torch.equal(got.cpu(), oracle.ext.furthest_point_sampling(mixed, 700))
+
+
+def test_fps_ordered_hint_with_non_finite_points(pkg, oracle, cuda):
+    x = cloud(91, 2, 1500)[..., :3].contiguous()
+    order = oracle.ext.furthest_point_sampling(x, 1500).long()
+    y = torch.gather(x, 1, order.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    y[0, 700, 1] = float("nan")
+    y[1, 3, 0] = float("inf")
+    want = oracle.ext.furthest_point_sampling(y, 600)
+    got, _ = pkg._ext.furthest_point_sampling_gather(y.to(cuda), 600, ordered=True)
+    assert torch.equal(got.cpu(), want)
