@@ -49,10 +49,10 @@ int* device_err_flag() {
 }
 
 // ---- run-time options ----------------------------------------------------------------------------
-static const char* const kOptName[OPT_COUNT] = {"fps_bucket", "bq_grid"};
-static const char* const kOptEnv[OPT_COUNT] = {"PN2_FPS_BUCKET", "PN2_BQ_GRID"};
-static const int kOptDefault[OPT_COUNT] = {0, 1};
-static int g_opt[OPT_COUNT] = {-1, -1};
+static const char* const kOptName[OPT_COUNT] = {"fps_bucket", "bq_grid", "sa_tiles_per_group"};
+static const char* const kOptEnv[OPT_COUNT] = {"PN2_FPS_BUCKET", "PN2_BQ_GRID", "PN2_SA_TILES_PER_GROUP"};
+static const int kOptDefault[OPT_COUNT] = {0, 1, 0};
+static int g_opt[OPT_COUNT] = {-1, -1, -1};
 
 int option_value(Option o) {
   int v = __atomic_load_n(&g_opt[o], __ATOMIC_RELAXED);
@@ -74,7 +74,7 @@ extern "C" int pn2_set_option(const char* name, int value) {
       return PN2_OK;
     }
   }
-  pn2::set_error("set_option: unknown option '%s' (known: fps_bucket, bq_grid)", name ? name : "(null)");
+  pn2::set_error("set_option: unknown option '%s' (known: fps_bucket, bq_grid, sa_tiles_per_group)", name ? name : "(null)");
   return PN2_ERR_INVALID;
 }
 

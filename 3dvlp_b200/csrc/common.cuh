@@ -51,7 +51,7 @@ inline int opt_n_threads(int work_size) {
 int sm_count();
 
 // run-time options (pn2_set_option); initial values come from the environment
-enum Option { OPT_FPS_BUCKET = 0, OPT_BQ_GRID = 1, OPT_COUNT = 2 };
+enum Option { OPT_FPS_BUCKET = 0, OPT_BQ_GRID = 1, OPT_SA_TILES_PER_GROUP = 2, OPT_COUNT = 3 };
 int option_value(Option o);
 
 // ---- device helpers -------------------------------------------------------------------------

@@ -717,6 +717,13 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
   const size_t smem = w_bytes + ng * x_bytes + 1024;
   long long grid = static_cast<long long>(sm_count()) * resident;
   if (grid * ng > tiles) grid = (tiles + ng - 1) / ng;
+  // pn2_set_option("sa_tiles_per_group", k): fewer persistent CTAs, each group claiming >= k tiles (counted
+  // before padded rows are dropped), so the per-CTA prologue (weight TMA, TMEM allocation) is paid less
+  // often -- for several batches in flight, where SM-time and not the latency of one launch counts
+  if (const int k = option_value(OPT_SA_TILES_PER_GROUP)) {
+    const long long capped = (tiles + static_cast<long long>(ng) * k - 1) / (static_cast<long long>(ng) * k);
+    if (capped < grid) grid = capped < 1 ? 1 : capped;
+  }
   cudaStream_t s = as_stream(stream);
   int rc;
   if (ng == 4) {

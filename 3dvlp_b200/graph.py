@@ -28,7 +28,11 @@ class GraphedBackbone:
         # separate streams); the default captures the low-latency 16-SM cluster FPS
         from . import _lib
         prev = _lib.get_option("fps_bucket")
+        prev_k = _lib.get_option("sa_tiles_per_group")
         _lib.set_option("fps_bucket", 1 if throughput else 0)
+        # throughput=True also launches the fused SA bodies on fewer persistent CTAs (>= 16 tiles per
+        # group): their per-CTA prologue is SM-time that other batches in flight could use
+        _lib.set_option("sa_tiles_per_group", (prev_k or 16) if throughput else 0)
         try:
             self.static_in = example_batch.clone().contiguous()
             self.graph = None
@@ -52,6 +56,7 @@ class GraphedBackbone:
                 torch.cuda.synchronize(self.static_in.device)
         finally:
             _lib.set_option("fps_bucket", prev)
+            _lib.set_option("sa_tiles_per_group", prev_k)
 
     def __call__(self, point_clouds):
         self.static_in.copy_(point_clouds, non_blocking=True)

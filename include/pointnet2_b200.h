@@ -41,7 +41,11 @@ int pn2_poll_device_error(int* flag_out, void* stream);
  *   "fps_bucket" [PN2_FPS_BUCKET, default 0]  1 = large scenes (16 384..50 176 points) use the single-SM
  *                bucketed FPS kernel with spatial pruning instead of the 16-SM cluster kernel: same
  *                output, ~2x the latency of one batch, 1/16 of the SM footprint (throughput mode);
- *   "bq_grid"    [PN2_BQ_GRID, default 1]     0 = ball query always uses the linear scan.
+ *   "bq_grid"    [PN2_BQ_GRID, default 1]     0 = ball query always uses the linear scan;
+ *   "sa_tiles_per_group" [PN2_SA_TILES_PER_GROUP, default 0]  k > 0 = pn2_sa_group_mlp launches fewer
+ *                persistent CTAs, each 128-thread group claiming >= k row tiles, so the per-CTA prologue
+ *                (weight TMA, TMEM allocation) is paid less often: same output, longer single launch,
+ *                less SM-time (throughput mode: several batches in flight).
  * pn2_get_option returns the value, or -1 for an unknown name. */
 int pn2_set_option(const char* name, int value);
 int pn2_get_option(const char* name);

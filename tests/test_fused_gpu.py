@@ -193,6 +193,53 @@ def test_graphed_backbone_replays_identically(pkg, cuda):
             assert torch.equal(v, want[k]), k
 
 
+@pytest.mark.parametrize("name", ["sa1_like", "sa2_like", "sa3_like", "sparse_balls_wide", "tiny"])
+def test_sa_tiles_per_group_option_is_bit_identical(pkg, cuda, name):
+    """pn2_set_option("sa_tiles_per_group", k) only changes how many persistent CTAs share the tiles
+    (throughput mode); tiles are claimed dynamically, the output must not move by a bit."""
+    from common import cloud, fill_state_dict
+    b, n, c_in, npoint, radius, ns, mlp = SA_CASES[name]
+    pc = cloud(100 + n, b, n, c_extra=c_in, extent=1.2, dup_frac=0.05, origin_pts=2)
+    xyz = pc[..., :3].contiguous().to(cuda)
+    feats = (pc[..., 3:].transpose(1, 2).contiguous() * 2.0 - 0.7).to(cuda) if c_in else None
+    m = pkg.PointnetSAModuleVotes(npoint=npoint, radius=radius, nsample=ns, mlp=[c_in] + mlp, use_xyz=True,
+                                  normalize_xyz=True)
+    fill_state_dict(m)
+    m = m.to(cuda).eval()
+    outs = []
+    try:
+        for k in (0, 1, 16, 1000):
+            pkg.set_option("sa_tiles_per_group", k)
+            assert pkg.get_option("sa_tiles_per_group") == k
+            with torch.no_grad():
+                _, nf, _ = m(xyz, feats)
+            outs.append(nf.clone())
+    finally:
+        pkg.set_option("sa_tiles_per_group", 0)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
+def test_throughput_graph_equals_latency_graph(pkg, cuda):
+    """GraphedBackbone(throughput=True) (bucketed FPS, fewer fused-SA CTAs) == the default graph."""
+    import importlib
+    from common import fill_state_dict
+    syn = importlib.import_module("3dvlp_b200.synthetic")
+    bb = pkg.Pointnet2Backbone(input_feature_dim=1)
+    fill_state_dict(bb)
+    bb = bb.to(cuda).eval()
+    a = syn.make_batch(3, 2, 20000, 1).to(cuda)
+    g0 = pkg.GraphedBackbone(bb, a)
+    g1 = pkg.GraphedBackbone(bb, a, throughput=True)
+    assert g0.graph is not None and g1.graph is not None
+    assert pkg.get_option("sa_tiles_per_group") == 0 and pkg.get_option("fps_bucket") == 0
+    o0 = {k: v.clone() for k, v in g0(a).items() if torch.is_tensor(v)}
+    o1 = g1(a)
+    torch.cuda.synchronize()
+    for k, v in o0.items():
+        assert torch.equal(v, o1[k]), k
+
+
 def test_sa_module_beyond_fused_limits_takes_generic_path(pkg, cuda):
     """More than 64 scenes per call (the fused kernel's row-plan limit) silently uses the op-by-op path:
     same indices, features within the mixed-precision tolerance of the fused result on the two halves."""
