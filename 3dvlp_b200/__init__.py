@@ -16,15 +16,16 @@ import sys as _sys
 
 from . import _lib  # noqa: F401
 from ._lib import get_option, set_option  # noqa: F401
-from . import _ext, backbone, nn_distance as _nn_distance_mod, pointnet2_modules, pointnet2_utils, pytorch_utils, voting, loss_detection, box_util, loss_grounding, contrast  # noqa: F401
+from . import _ext, backbone, nn_distance as _nn_distance_mod, pointnet2_modules, pointnet2_utils, pytorch_utils, voting, loss_detection, box_util, loss_grounding, contrast, proposal  # noqa: F401
 from .backbone import Pointnet2Backbone  # noqa: F401
 from .graph import GraphedBackbone  # noqa: F401
 from .nn_distance import huber_loss, knn_distance, nn_distance  # noqa: F401
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes  # noqa: F401
 from .voting import VoteNetFrontEnd, VotingModule  # noqa: F401
 from .contrast import ContrastModule  # noqa: F401
+from .proposal import ProposalModule, StandardROIHeads, VoteNetDetector  # noqa: F401
 
-__all__ = ["Pointnet2Backbone", "GraphedBackbone", "VotingModule", "VoteNetFrontEnd", "PointnetSAModuleVotes", "PointnetFPModule", "nn_distance", "huber_loss",
+__all__ = ["Pointnet2Backbone", "GraphedBackbone", "VotingModule", "VoteNetFrontEnd", "ProposalModule", "StandardROIHeads", "VoteNetDetector", "PointnetSAModuleVotes", "PointnetFPModule", "nn_distance", "huber_loss",
            "knn_distance", "pointnet2_utils", "pointnet2_modules", "pytorch_utils", "install_dropin"]
 
 
@@ -46,9 +47,12 @@ def install_dropin():
         "utils.nn_distance": _nn_distance_mod,
         "models.base_module.voting_module": voting,
         "models.base_module.backbone_module": backbone,
+        "models.proposal_module.proposal_module_fcos": proposal,
+        "models.proposal_module.ROI_heads.roi_heads": proposal,
     }
     import importlib
-    for parent in ("pointnet2", "lib", "lib.pointnet2", "utils", "models", "models.base_module"):
+    for parent in ("pointnet2", "lib", "lib.pointnet2", "utils", "models", "models.base_module",
+                   "models.proposal_module", "models.proposal_module.ROI_heads"):
         if parent in _sys.modules:
             continue
         try:  # keep the caller's real packages (the reference's lib/ and utils/ are namespace packages)
