@@ -518,6 +518,38 @@ def main():
                 del fgraphs
             except Exception as ex:
                 line["votenet_front_end"] = {"error": repr(ex)[:200]}
+            try:  # configs[1] to the end of the detection branch: + ROI head + box decode (ProposalModule)
+                import numpy as np
+                det = pkg.VoteNetDetector(input_feature_dim=C_IN, mean_size_arr=np.ones((18, 3), dtype=np.float32))
+                det.backbone_net = model
+                det.vgen = fe.vgen
+                det.proposal.vote_aggregation = fe.proposal.vote_aggregation
+                syn.randomize_bn_stats(det.proposal.proposal)
+                det = det.eval().to(dev)
+                dgraphs = [pkg.GraphedBackbone(det, dev_pool[0], throughput=throughput_mode) for _ in range(depth)]
+                if all(g.graph is not None for g in dgraphs):
+                    def det_steps(count):
+                        for st in lanes:
+                            st.wait_stream(main_stream)
+                        for s in range(count):
+                            with torch.cuda.stream(lanes[s % depth]):
+                                dgraphs[s % depth](dev_pool[s % POOL])
+                        for st in lanes:
+                            main_stream.wait_stream(st)
+                    det_steps(4 * depth)
+                    torch.cuda.synchronize()
+                    v0.record()
+                    det_steps(200)
+                    v1.record()
+                    torch.cuda.synchronize()
+                    dms = v0.elapsed_time(v1) / 200
+                    line["votenet_detector"] = {"value": SCENES_PER_GPU / (dms * 1e-3), "unit": "scenes/s",
+                                                "ms_per_step": dms, "batches_in_flight": depth,
+                                                "what": "backbone + VotingModule + ProposalModule (vote aggregation, ROI head, "
+                                                        "box decode to 256 x 8 corners), CUDA-graph replays"}
+                del dgraphs
+            except Exception as ex:
+                line["votenet_detector"] = {"error": repr(ex)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             cores = os.cpu_count() or 1
