@@ -109,11 +109,24 @@ def roty_batch_pytorch(t):
 _CORNER_SIGNS = ((1, 1, 1), (1, -1, 1), (-1, -1, 1), (-1, 1, 1), (1, 1, -1), (1, -1, -1), (-1, -1, -1), (-1, 1, -1))
 
 
+_SIGNS_CACHE = {}
+
+
+def _corner_signs(device, dtype):
+    """The (8,3) sign table, uploaded once per device: a host->device copy of a Python list inside a CUDA
+    graph capture would be illegal, and the detector's box decode is captured."""
+    key = (str(device), dtype)
+    t = _SIGNS_CACHE.get(key)
+    if t is None:
+        t = _SIGNS_CACHE[key] = torch.tensor(_CORNER_SIGNS, dtype=dtype).to(device)
+    return t
+
+
 def get_3d_box_batch(box_size, heading_angle, center):
     """box_util.py:361-384 on the device: box_size (...,3), heading_angle (...), center (...,3) ->
     corners (...,8,3).  Keeps the reference's quirk of rotating with ``roty_batch`` over corners laid
     out (l, w, h) (its own comment: "Actually we should rotz"); ScanNet headings are 0."""
-    signs = torch.tensor(_CORNER_SIGNS, device=box_size.device, dtype=box_size.dtype)      # (8,3)
+    signs = _corner_signs(box_size.device, box_size.dtype)                                   # (8,3)
     corners = box_size.unsqueeze(-2) * 0.5 * signs                                           # (...,8,3)
     R = roty_batch_pytorch(heading_angle.to(box_size.dtype))                                 # (...,3,3)
     return torch.matmul(corners, R.transpose(-1, -2)) + center.unsqueeze(-2)

@@ -90,7 +90,7 @@ class StandardROIHeads(nn.Module):
             at += w.shape[0]
             ws.append(w)
             bs.append(b)
-        n = (at + 15) // 16 * 16  # the linear kernel's N granularity
+        n = max(64, (at + 15) // 16 * 16)  # the linear kernel's N granularity; one 64-wide panel at least
         wh = torch.zeros(n, 128, device=w1.device)
         bh = torch.zeros(n, device=w1.device)
         wh[:at] = torch.cat(ws, 0)

@@ -441,6 +441,12 @@ def main():
                         "note": "FPS is latency/ALU-bound by construction (2047 dependent rounds); see alu_frac",
                         "alu_gflops": updates * 10 / t_fps / 1e9, "alu_frac": updates * 10 / t_fps / 74.5e12,
                         "us_per_sample": ops[fps_key] * 1e3 / 2047}
+            # the kernel holds 1 SM per scene (bucketed) or a 16-CTA cluster per scene: the fp32 rate of the
+            # algorithmic updates against the peak of the SMs it actually occupies (pruning in the bucketed
+            # kernel executes fewer updates than the algorithm counts, so this can approach or pass 1)
+            sms = SCENES_PER_GPU * (1 if throughput_mode else 16)
+            roofline["sms_occupied"] = sms
+            roofline["alu_frac_of_occupied_sms"] = roofline["alu_frac"] * 148.0 / sms
         work = algorithmic_work()
         for (name, k), v in sorted(ops.items(), key=lambda kv: -kv[1]):
             row = {"call": name, "nth": k, "ms": round(v, 4), "share_of_forward": round(v / sum(ops.values()), 4)}

@@ -95,13 +95,13 @@ def test_proposal_fused_path(pkg, gold, cuda, tag, nh, kl):
         got = d[k].float().cpu().numpy()
         assert got.shape == want.shape, k
         scale = max(float(np.abs(want).max()), 1e-6)
-        assert float(np.abs(got - want).max()) < 3e-2 * scale, (k, float(np.abs(got - want).max()), scale)
+        assert float(np.abs(got - want).max()) < 5e-2 * scale, (k, float(np.abs(got - want).max()), scale)
     # labels may flip only where the two logits are within the contract's error of each other
     for k, src in (("bbox_mask", "objectness_scores"), ("pred_bbox_sems", "sem_cls_scores")):
         want, got = gold[f"{tag}_{k}"], d[k].cpu().numpy()
         s = np.sort(gold[f"{tag}_{src}"], -1)
         margin = s[..., -1] - s[..., -2]
-        bad = (got != want) & (margin > 6e-2 * np.abs(gold[f"{tag}_{src}"]).max())
+        bad = (got != want) & (margin > 1e-1 * np.abs(gold[f"{tag}_{src}"]).max())
         assert not bad.any(), k
     # corners are consistent with the decoded centre / size / heading (exact functional relation)
     from importlib import import_module
