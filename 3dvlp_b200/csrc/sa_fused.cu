@@ -28,6 +28,13 @@
 namespace pn2 {
 namespace {
 
+// max of three floats in one instruction (FMNMX3, sm_100+); NaN operands are ignored like fmaxf
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 constexpr int SA_THREADS = 128;
 constexpr int kMaxScenes = 64;  // scenes per launch
 
@@ -439,13 +446,23 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
         tc::tmem_ld16(lane_base + c0, v);
         const uint32_t bits = (endm[c0 >> 5] >> (c0 & 31)) & 0xffffu;
         const int cidq = (c0 & 64) ? ((c0 & 32) ? cid[3] : cid[2]) : ((c0 & 32) ? cid[1] : cid[0]);
+        // four columns at a time: where no centre ends inside them (the common case: 28 / 7 / 14 rows per
+        // centre in SA1 / SA2 / SA3-4) the running max is two 3-input FMNMX3 and one warp-uniform test
+        // instead of four max + four tests; max is exact, so the grouping cannot change a bit
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          mx = fmaxf(mx, v[i]);
-          if (bits & (1u << i)) {
-            const int jg = __shfl_sync(0xffffffffu, cidq, (c0 + i) & 31) >> a.ns_shift;
-            asm volatile("red.global.max.s32 [%0], %1;" ::"l"(out_bits + jg), "r"(__float_as_int(fmaxf(mx + bias, 0.f))) : "memory");
-            mx = -INFINITY;
+        for (int q4 = 0; q4 < 4; ++q4) {
+          if (((bits >> (4 * q4)) & 0xfu) == 0u) {
+            mx = fmax3(fmax3(mx, v[4 * q4], v[4 * q4 + 1]), v[4 * q4 + 2], v[4 * q4 + 3]);
+          } else {
+#pragma unroll
+            for (int i = 4 * q4; i < 4 * q4 + 4; ++i) {
+              mx = fmaxf(mx, v[i]);
+              if (bits & (1u << i)) {
+                const int jg = __shfl_sync(0xffffffffu, cidq, (c0 + i) & 31) >> a.ns_shift;
+                asm volatile("red.global.max.s32 [%0], %1;" ::"l"(out_bits + jg), "r"(__float_as_int(fmaxf(mx + bias, 0.f))) : "memory");
+                mx = -INFINITY;
+              }
+            }
           }
         }
       }
