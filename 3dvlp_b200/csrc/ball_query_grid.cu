@@ -128,7 +128,7 @@ bq_query_kernel(int n, int m, float radius2, float inv_h, uint32_t mask, int nsa
                 const float* __restrict__ new_xyz, const float* __restrict__ xyz, const int* __restrict__ start,
                 const float4* __restrict__ sorted, int* __restrict__ idx) {
   __shared__ int s_begin[BQ_QWARPS][27], s_off[BQ_QWARPS][28];
-  __shared__ int s_hits[BQ_QWARPS][BQ_CAP];
+  __shared__ __align__(16) int s_hits[BQ_QWARPS][BQ_CAP + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int scene = blockIdx.y;
   const int j = blockIdx.x * BQ_QWARPS + warp;
@@ -140,10 +140,17 @@ bq_query_kernel(int n, int m, float radius2, float inv_h, uint32_t mask, int nsa
   int* row = idx + (static_cast<size_t>(scene) * m + j) * nsample;
   const int bx = cell_of(cx, inv_h), by = cell_of(cy, inv_h), bz = cell_of(cz, inv_h);
 
-  // lanes 0..26: range of one neighbouring cell each
+  // lanes 0..26: range of one neighbouring cell each.  Every BUCKET is scanned once: when two of the 27
+  // cells hash to the same bucket only the lowest lane keeps it.  A point within the radius lives in one
+  // of the 27 cells (cell edge > radius), hence in exactly one of the scanned buckets, so it is found
+  // exactly once; strangers that share a bucket through a hash collision fail the distance test like
+  // any other far point.  (No per-candidate "is it in the probed cell" test: that was 19 % of the
+  // kernel's instructions.)
   int begin = 0, count = 0;
-  if (lane < 27) {
-    const uint32_t bkt = cell_hash(bx + lane % 3 - 1, by + (lane / 3) % 3 - 1, bz + lane / 9 - 1, mask);
+  uint32_t bkt = 0x80000000u | static_cast<uint32_t>(lane);  // lanes 27..31: unique, matches nothing
+  if (lane < 27) bkt = cell_hash(bx + lane % 3 - 1, by + (lane / 3) % 3 - 1, bz + lane / 9 - 1, mask);
+  const uint32_t same = __match_any_sync(0xffffffffu, bkt);
+  if (lane < 27 && (same & ((1u << lane) - 1u)) == 0u) {
     begin = __ldg(st + bkt);
     count = __ldg(st + bkt + 1) - begin;
   }
@@ -173,11 +180,7 @@ bq_query_kernel(int n, int m, float radius2, float inv_h, uint32_t mask, int nsa
         if (s_off[warp][mid] <= q) lo = mid; else hi = mid - 1;
       }
       const float4 p = __ldg(pts + s_begin[warp][lo] + (q - s_off[warp][lo]));
-      // the candidate must live in the probed cell: drops hash-collision strangers and guarantees
-      // that a point reachable through two colliding cells is counted once
-      const bool mine = cell_of(p.x, inv_h) == bx + lo % 3 - 1 && cell_of(p.y, inv_h) == by + (lo / 3) % 3 - 1 &&
-                        cell_of(p.z, inv_h) == bz + lo / 9 - 1;
-      hit = mine && (sqdist3(cx - p.x, cy - p.y, cz - p.z) < radius2);
+      hit = sqdist3(cx - p.x, cy - p.y, cz - p.z) < radius2;
       pidx = __float_as_int(p.w);
     }
     const uint32_t mk = __ballot_sync(0xffffffffu, hit);
@@ -196,10 +199,17 @@ bq_query_kernel(int n, int m, float radius2, float inv_h, uint32_t mask, int nsa
   if (nhit <= BQ_CAP) {
     // rank the hits by point index: slot[rank] = index, padding with the rank-0 hit
     int first = 0x7fffffff;
+    if (lane < 4) s_hits[warp][nhit + lane] = 0x7fffffff;  // pad to a multiple of four: never "smaller"
+    __syncwarp();
+    const int4* h4 = reinterpret_cast<const int4*>(s_hits[warp]);
+    const int n4 = (nhit + 3) >> 2;
     for (int i = lane; i < nhit; i += 32) {
       const int mine = s_hits[warp][i];
       int rank = 0;
-      for (int t = 0; t < nhit; ++t) rank += (s_hits[warp][t] < mine) ? 1 : 0;
+      for (int t = 0; t < n4; ++t) {  // one broadcast LDS.128 per four hits
+        const int4 h = h4[t];
+        rank += (h.x < mine) + (h.y < mine) + (h.z < mine) + (h.w < mine);
+      }
       if (rank < nsample) row[rank] = mine;
       if (rank == 0) first = mine;
     }
