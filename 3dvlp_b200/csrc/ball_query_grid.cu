@@ -123,20 +123,17 @@ __global__ void bq_scatter_kernel(int n, float inv_h, uint32_t mask, const float
   sorted[static_cast<size_t>(scene) * n + pos] = make_float4(x, y, z, __int_as_float(k));
 }
 
-__global__ void __launch_bounds__(BQ_QWARPS * 32)
-bq_query_kernel(int n, int m, float radius2, float inv_h, uint32_t mask, int nsample,
-                const float* __restrict__ new_xyz, const float* __restrict__ xyz, const int* __restrict__ start,
-                const float4* __restrict__ sorted, int* __restrict__ idx) {
-  __shared__ int s_begin[BQ_QWARPS][27], s_off[BQ_QWARPS][28];
-  __shared__ __align__(16) int s_hits[BQ_QWARPS][BQ_CAP + 4];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int scene = blockIdx.y;
-  const int j = blockIdx.x * BQ_QWARPS + warp;
-  if (j >= m) return;  // warp-uniform
+// One centre, one warp.  SMEM: `st` / `pts` are the shared-memory grid of bq_small_kernel, otherwise the
+// global workspace of ball_query_grid.  A centre whose 27-cell stencil holds more than `max_total`
+// candidates, or more than BQ_CAP hits, takes the ordered linear scan over the original cloud.
+template <bool SMEM>
+__device__ __forceinline__ void bq_query_centre(int n, int m, int scene, int j, float radius2, float inv_h, uint32_t mask,
+                                                int nsample, int max_total, const float* __restrict__ new_xyz,
+                                                const float* __restrict__ xyz, const int* st, const float4* pts,
+                                                int* __restrict__ idx, int* s_begin, int* s_off, int* s_hits) {
+  const int lane = threadIdx.x & 31;
   const float* c = new_xyz + (static_cast<size_t>(scene) * m + j) * 3;
   const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
-  const int* st = start + static_cast<size_t>(scene) * (mask + 2);
-  const float4* pts = sorted + static_cast<size_t>(scene) * n;
   int* row = idx + (static_cast<size_t>(scene) * m + j) * nsample;
   const int bx = cell_of(cx, inv_h), by = cell_of(cy, inv_h), bz = cell_of(cz, inv_h);
 
@@ -151,8 +148,8 @@ bq_query_kernel(int n, int m, float radius2, float inv_h, uint32_t mask, int nsa
   if (lane < 27) bkt = cell_hash(bx + lane % 3 - 1, by + (lane / 3) % 3 - 1, bz + lane / 9 - 1, mask);
   const uint32_t same = __match_any_sync(0xffffffffu, bkt);
   if (lane < 27 && (same & ((1u << lane) - 1u)) == 0u) {
-    begin = __ldg(st + bkt);
-    count = __ldg(st + bkt + 1) - begin;
+    begin = SMEM ? st[bkt] : __ldg(st + bkt);
+    count = (SMEM ? st[bkt + 1] : __ldg(st + bkt + 1)) - begin;
   }
   int incl = count;
 #pragma unroll
@@ -161,13 +158,15 @@ bq_query_kernel(int n, int m, float radius2, float inv_h, uint32_t mask, int nsa
     if (lane >= o) incl += v;
   }
   const int total = __shfl_sync(0xffffffffu, incl, 26);
-  if (lane < 27) { s_begin[warp][lane] = begin; s_off[warp][lane] = incl - count; }
-  if (lane == 27) s_off[warp][27] = total;
+  if (lane < 27) { s_begin[lane] = begin; s_off[lane] = incl - count; }
+  if (lane == 27) s_off[27] = total;
   __syncwarp();
 
   const uint32_t lt = (1u << lane) - 1u;
   int nhit = 0;
-  for (int q0 = 0; q0 < total; q0 += 32) {
+  const bool use_grid = total <= max_total;  // warp-uniform
+  if (!use_grid) nhit = BQ_CAP + 1;          // -> the ordered linear scan below
+  for (int q0 = 0; use_grid && q0 < total; q0 += 32) {
     const int q = q0 + lane;
     bool hit = false;
     int pidx = 0;
@@ -177,16 +176,17 @@ bq_query_kernel(int n, int m, float radius2, float inv_h, uint32_t mask, int nsa
 #pragma unroll
       for (int it = 0; it < 5; ++it) {
         const int mid = (lo + hi + 1) >> 1;
-        if (s_off[warp][mid] <= q) lo = mid; else hi = mid - 1;
+        if (s_off[mid] <= q) lo = mid; else hi = mid - 1;
       }
-      const float4 p = __ldg(pts + s_begin[warp][lo] + (q - s_off[warp][lo]));
+      const float4* pp = pts + s_begin[lo] + (q - s_off[lo]);
+      const float4 p = SMEM ? *pp : __ldg(pp);
       hit = sqdist3(cx - p.x, cy - p.y, cz - p.z) < radius2;
       pidx = __float_as_int(p.w);
     }
     const uint32_t mk = __ballot_sync(0xffffffffu, hit);
     if (hit) {
       const int pos = nhit + __popc(mk & lt);
-      if (pos < BQ_CAP) s_hits[warp][pos] = pidx;
+      if (pos < BQ_CAP) s_hits[pos] = pidx;
     }
     nhit += __popc(mk);
   }
@@ -199,12 +199,12 @@ bq_query_kernel(int n, int m, float radius2, float inv_h, uint32_t mask, int nsa
   if (nhit <= BQ_CAP) {
     // rank the hits by point index: slot[rank] = index, padding with the rank-0 hit
     int first = 0x7fffffff;
-    if (lane < 4) s_hits[warp][nhit + lane] = 0x7fffffff;  // pad to a multiple of four: never "smaller"
+    if (lane < 4) s_hits[nhit + lane] = 0x7fffffff;  // pad to a multiple of four: never "smaller"
     __syncwarp();
-    const int4* h4 = reinterpret_cast<const int4*>(s_hits[warp]);
+    const int4* h4 = reinterpret_cast<const int4*>(s_hits);
     const int n4 = (nhit + 3) >> 2;
     for (int i = lane; i < nhit; i += 32) {
-      const int mine = s_hits[warp][i];
+      const int mine = s_hits[i];
       int rank = 0;
       for (int t = 0; t < n4; ++t) {  // one broadcast LDS.128 per four hits
         const int4 h = h4[t];
@@ -233,6 +233,109 @@ bq_query_kernel(int n, int m, float radius2, float inv_h, uint32_t mask, int nsa
     }
   }
   for (int s = min(cnt, nsample) + lane; s < nsample; s += 32) row[s] = first;
+}
+
+__global__ void __launch_bounds__(BQ_QWARPS * 32)
+bq_query_kernel(int n, int m, float radius2, float inv_h, uint32_t mask, int nsample,
+                const float* __restrict__ new_xyz, const float* __restrict__ xyz, const int* __restrict__ start,
+                const float4* __restrict__ sorted, int* __restrict__ idx) {
+  __shared__ int s_begin[BQ_QWARPS][27], s_off[BQ_QWARPS][28];
+  __shared__ __align__(16) int s_hits[BQ_QWARPS][BQ_CAP + 4];
+  const int warp = threadIdx.x >> 5;
+  const int scene = blockIdx.y;
+  const int j = blockIdx.x * BQ_QWARPS + warp;
+  if (j >= m) return;  // warp-uniform
+  bq_query_centre<false>(n, m, scene, j, radius2, inv_h, mask, nsample, 0x7fffffff, new_xyz, xyz,
+                         start + static_cast<size_t>(scene) * (mask + 2), sorted + static_cast<size_t>(scene) * n, idx,
+                         s_begin[warp], s_off[warp], s_hits[warp]);
+}
+
+// ---- small clouds (2048 <= n <= 4096: SA2 of the backbone) -------------------------------------------
+// The linear scan of search.cu tests all n points per centre and only stops early when a ball fills up;
+// SA2's balls hold 7 of 32 samples, so every centre pays the full scan (12.8 M warp-instructions per
+// step, the third-largest kernel by instruction count).  For clouds this small the whole grid fits in
+// shared memory: a CTA of 1024 threads counting-sorts its scene into SM_T hashed buckets (count ->
+// block scan -> scatter, all in shared memory), then each of its 32 warps answers SM_CPW centres out
+// of it with the same per-centre routine as the large-cloud kernel.  A centre whose stencil holds more
+// than n/8 candidates (large radius relative to the scene: the grid would not pay) takes the ordered
+// linear scan instead, so the choice is made per centre, on the device, with identical output.
+constexpr int SM_T = 2048;       // buckets of the shared-memory grid
+constexpr int SM_WARPS = 32;
+constexpr int SM_CPW = 8;        // centres per warp
+constexpr int SM_MAXN = 4096;
+
+__global__ void __launch_bounds__(SM_WARPS * 32)
+bq_small_kernel(int n, int m, float radius2, float inv_h, int nsample, const float* __restrict__ new_xyz,
+                const float* __restrict__ xyz, int* __restrict__ idx) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  float4* s_pts = reinterpret_cast<float4*>(sm_raw);                       // [n]
+  int* s_start = reinterpret_cast<int*>(s_pts + n);                         // [SM_T + 1]
+  int* s_cur = s_start + SM_T + 1;                                          // [SM_T]
+  int* s_wsum = s_cur + SM_T;                                               // [32]
+  int* s_begin = s_wsum + 32;                                               // [SM_WARPS][27]
+  int* s_off = s_begin + SM_WARPS * 27;                                     // [SM_WARPS][28]
+  int* s_hits = s_off + SM_WARPS * 28 + 3;                                  // [SM_WARPS][BQ_CAP + 4], 16-byte aligned
+  s_hits = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(s_hits)) & ~static_cast<uintptr_t>(15));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int scene = blockIdx.y;
+  const float* P = xyz + static_cast<size_t>(scene) * n * 3;
+  constexpr uint32_t mask = SM_T - 1;
+
+  for (int i = tid; i < SM_T; i += SM_WARPS * 32) s_cur[i] = 0;
+  __syncthreads();
+  float px[4], py[4], pz[4];
+  uint32_t pb[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int k = tid + u * SM_WARPS * 32;
+    if (k < n) {
+      px[u] = __ldg(P + 3 * k); py[u] = __ldg(P + 3 * k + 1); pz[u] = __ldg(P + 3 * k + 2);
+      pb[u] = cell_hash(cell_of(px[u], inv_h), cell_of(py[u], inv_h), cell_of(pz[u], inv_h), mask);
+      atomicAdd(s_cur + pb[u], 1);
+    }
+  }
+  __syncthreads();
+  {  // exclusive scan of the SM_T counts: two per thread, warp scan, scan of the 32 warp sums
+    const int c0 = s_cur[2 * tid], c1 = s_cur[2 * tid + 1];
+    int inc = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      s_wsum[lane] = w;
+    }
+    __syncthreads();
+    const int excl = (warp ? s_wsum[warp - 1] : 0) + inc - (c0 + c1);
+    s_start[2 * tid] = excl; s_start[2 * tid + 1] = excl + c0;
+    s_cur[2 * tid] = excl; s_cur[2 * tid + 1] = excl + c0;
+    if (tid == 0) s_start[SM_T] = n;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int k = tid + u * SM_WARPS * 32;
+    if (k < n) s_pts[atomicAdd(s_cur + pb[u], 1)] = make_float4(px[u], py[u], pz[u], __int_as_float(k));
+  }
+  __syncthreads();
+
+  const int j0 = blockIdx.x * (SM_WARPS * SM_CPW);
+  for (int i = 0; i < SM_CPW; ++i) {
+    const int j = j0 + i * SM_WARPS + warp;
+    if (j >= m) break;  // warp-uniform
+    bq_query_centre<true>(n, m, scene, j, radius2, inv_h, mask, nsample, n >> 3, new_xyz, xyz, s_start, s_pts, idx,
+                          s_begin + warp * 27, s_off + warp * 28, s_hits + warp * (BQ_CAP + 4));
+    __syncwarp();
+  }
 }
 
 }  // namespace
@@ -283,5 +386,20 @@ int ball_query_grid(int b, int n, int m, float radius, int nsample, const float*
   cudaFreeAsync(ws, s);
   return rc;
 }
+
+// Called by pn2_ball_query (search.cu) for clouds of 2048..4096 points: one launch, grid in shared memory.
+int ball_query_small(int b, int n, int m, float radius, int nsample, const float* new_xyz, const float* xyz,
+                     int* idx, cudaStream_t s) {
+  const float h = fabsf(radius) * 1.001f;
+  const size_t smem = static_cast<size_t>(n) * sizeof(float4) +
+                      (static_cast<size_t>(SM_T) * 2 + 1 + 32 + SM_WARPS * 55 + 4 + SM_WARPS * (BQ_CAP + 4)) * sizeof(int) + 16;
+  PN2_CUDA(cudaFuncSetAttribute(bq_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  dim3 grid((m + SM_WARPS * SM_CPW - 1) / (SM_WARPS * SM_CPW), b);
+  bq_small_kernel<<<grid, SM_WARPS * 32, smem, s>>>(n, m, radius * radius, 1.0f / h, nsample, new_xyz, xyz, idx);
+  PN2_CHECK_LAUNCH("bq_small_kernel");
+  return PN2_OK;
+}
+
+bool ball_query_small_supported(int n) { return n >= 2048 && n <= SM_MAXN; }
 
 }  // namespace pn2

@@ -142,6 +142,9 @@ three_nn_kernel(int n, int m, const float* __restrict__ unknown, const float* __
 
 int ball_query_grid(int b, int n, int m, float radius, int nsample, const float* new_xyz, const float* xyz,
                     int* idx, cudaStream_t s);  // ball_query_grid.cu
+int ball_query_small(int b, int n, int m, float radius, int nsample, const float* new_xyz, const float* xyz,
+                     int* idx, cudaStream_t s);  // ball_query_grid.cu: grid in shared memory, 2048 <= n < 4096
+bool ball_query_small_supported(int n);
 
 }  // namespace pn2
 
@@ -156,6 +159,11 @@ extern "C" int pn2_ball_query(int b, int n, int m, float radius, int nsample, co
   // pn2_set_option("bq_grid", 0) / PN2_BQ_GRID=0 forces the linear scan
   if (option_value(OPT_BQ_GRID) && n >= 4096 && radius2 > 0.f && std::isfinite(radius) && fabsf(radius) > 1e-6f)
     return ball_query_grid(b, n, m, radius, nsample, new_xyz, xyz, idx, as_stream(stream));
+  // mid-sized clouds (SA2): the same search out of a grid built in shared memory, one launch; a centre
+  // whose stencil would hold more than n/8 candidates scans linearly inside that kernel
+  if (option_value(OPT_BQ_GRID) && ball_query_small_supported(n) && radius2 > 0.f && std::isfinite(radius) &&
+      fabsf(radius) > 1e-6f)
+    return ball_query_small(b, n, m, radius, nsample, new_xyz, xyz, idx, as_stream(stream));
   const int per_cta = BQ_CPW * BQ_WARPS;
   dim3 grid((m + per_cta - 1) / per_cta, b);
   ball_query_kernel<<<grid, BQ_WARPS * 32, 0, as_stream(stream)>>>(n, m, radius2, nsample, new_xyz, xyz, idx);

@@ -113,6 +113,35 @@ def test_ball_query_grid_path_bit_exact(pkg, oracle, cuda, n, m, r, ns):
     assert torch.equal(got.cpu(), want)
 
 
+@pytest.mark.parametrize("n,m,r,ns", [(2048, 1024, 0.4, 32), (2048, 300, 0.05, 8), (3000, 513, 0.3, 64),
+                                      (4095, 77, 0.15, 16), (2500, 256, 5.0, 16), (2048, 1, 0.6, 128),
+                                      (3500, 1000, 1.2, 16)])
+def test_ball_query_shared_grid_path_bit_exact(pkg, oracle, cuda, n, m, r, ns):
+    """2048 <= n < 4096 (SA2 of the backbone) builds the hashed grid in shared memory, one launch; a
+    centre whose 27-cell stencil holds more than n/8 candidates (large radius, dense cluster) or more
+    than 256 hits scans linearly inside the kernel.  Bit-exact either way, and equal to the plain
+    linear-scan kernel (option bq_grid = 0)."""
+    x = cloud(250 + n, 3, n, extent=1.5, dup_frac=0.2, origin_pts=3)[..., :3].contiguous()
+    x[:, : n // 10] = x[:, :1] + 0.01 * torch.randn(3, n // 10, 3, generator=torch.Generator().manual_seed(n))
+    c = x[:, torch.randperm(n, generator=torch.Generator().manual_seed(n))[:m]].contiguous()
+    c[:, 0] = 50.0          # empty ball
+    if m > 1:
+        c[:, 1] = x[:, 0]   # centre inside the dense cluster
+    want = oracle.ext.ball_query(c, x, r, ns)
+    got = pkg._ext.ball_query(c.to(cuda), x.to(cuda), r, ns)
+    assert torch.equal(got.cpu(), want)
+    try:
+        pkg.set_option("bq_grid", 0)
+        lin = pkg._ext.ball_query(c.to(cuda), x.to(cuda), r, ns)
+    finally:
+        pkg.set_option("bq_grid", 1)
+    assert torch.equal(lin.cpu(), want)
+    # a far-away, negative-coordinate copy of the scene hashes differently and must give the same rows
+    off = torch.tensor([-37.5, 12.25, -3.0])
+    got2 = pkg._ext.ball_query((c + off).contiguous().to(cuda), (x + off).contiguous().to(cuda), r, ns)
+    assert torch.equal(got2.cpu(), oracle.ext.ball_query((c + off).contiguous(), (x + off).contiguous(), r, ns))
+
+
 def test_ball_query_grid_scene_40k(pkg, oracle, cuda):
     import importlib
     syn = importlib.import_module("3dvlp_b200.synthetic")
