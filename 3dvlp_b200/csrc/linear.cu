@@ -178,6 +178,32 @@ pack_rows_kernel(int c, int n, int kpad, const float* __restrict__ f, __nv_bfloa
   }
 }
 
+// The same transpose with a 64-channel x 32-point tile: a thread converts eight consecutive channels of
+// one point and writes them with ONE 16-byte store (eight lanes cover a point's 128 contiguous bytes),
+// instead of four 2-byte stores: 0.27 instead of 1.3 warp-instructions per element.  kpad % 8 == 0.
+__global__ void __launch_bounds__(256)
+pack_rows64_kernel(int c, int n, int kpad, const float* __restrict__ f, __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[64][33];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* src = f + static_cast<size_t>(b) * c * n;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = c0 + ty + 8 * i, p = p0 + tx;
+    tile[ty + 8 * i][tx] = (ch < c && p < n) ? __ldg(src + static_cast<size_t>(ch) * n + p) : 0.f;
+  }
+  __syncthreads();
+  const int chunk = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int p = p0 + pl, ch0 = c0 + chunk * 8;
+  if (p < n && ch0 < kpad) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = tile[chunk * 8 + i][pl];
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * n + p) * kpad + ch0) =
+        make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]), tc::pack_bf16(v[6], v[7]));
+  }
+}
+
 // point-major rows of the input cloud, (rows, ld) fp32 with the features in columns [col0, col0+c),
 // -> (rows, kpad) bf16 zero padded: thread = 8 output channels (one 16-byte store)
 __global__ void __launch_bounds__(256)
@@ -214,8 +240,13 @@ extern "C" int pn2_pack_weight_bf16(int n, int k, int kpad, const float* w, void
 
 extern "C" int pn2_pack_rows_bf16(int b, int c, int n, int kpad, const float* features, void* out, void* stream) {
   PN2_REQUIRE(b > 0 && c > 0 && n > 0 && kpad >= c && features && out && b <= 65535, "pack_rows_bf16: bad arguments");
-  dim3 grid((n + 31) / 32, (kpad + 31) / 32, b);
-  pack_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(c, n, kpad, features, static_cast<__nv_bfloat16*>(out));
+  if (kpad % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    dim3 grid((n + 31) / 32, (kpad + 63) / 64, b);
+    pack_rows64_kernel<<<grid, 256, 0, as_stream(stream)>>>(c, n, kpad, features, static_cast<__nv_bfloat16*>(out));
+  } else {
+    dim3 grid((n + 31) / 32, (kpad + 31) / 32, b);
+    pack_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(c, n, kpad, features, static_cast<__nv_bfloat16*>(out));
+  }
   PN2_CHECK_LAUNCH("pack_rows_kernel");
   return PN2_OK;
 }

@@ -50,6 +50,14 @@ def test_pack_rows(pkg, cuda):
     want = torch.zeros(3, 777, 192, device=cuda)
     want[:, :, :131] = f.transpose(1, 2)
     assert torch.equal(p.float().view(3, 777, 192), bf16r(want))
+    # a width that is not a multiple of eight takes the scalar-store kernel; exact tile multiples too
+    p2 = tcm.pack_rows(f, kpad=132)
+    assert torch.equal(p2.float().view(3, 777, 132), bf16r(want[:, :, :132]))
+    g = torch.randn(2, 128, 2048, device=cuda)
+    assert torch.equal(tcm.pack_rows(g).float().view(2, 2048, 128), bf16r(g.transpose(1, 2)))
+    h = torch.randn(1, 5, 33, device=cuda)
+    p3 = tcm.pack_rows(h)
+    assert p3.shape == (33, 64) and torch.equal(p3.float()[:, :5], bf16r(h[0].t())) and p3.float()[:, 5:].eq(0).all()
 
 
 SA_CASES = {
