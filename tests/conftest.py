@@ -16,8 +16,14 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def pkg():
-    """The product package (its name starts with a digit, hence import_module)."""
-    return importlib.import_module("3dvlp_b200")
+    """The product package (its name starts with a digit, hence import_module).  The CUDA library is a
+    git-ignored build artefact: on a fresh checkout with nvcc present it is compiled here once (this
+    builds the product, it is not a fallback -- without the library every op still fails loudly)."""
+    import shutil
+    p = importlib.import_module("3dvlp_b200")
+    if not os.path.exists(p._lib.LIB_PATH) and shutil.which("nvcc"):
+        importlib.import_module("3dvlp_b200.build").build()
+    return p
 
 
 @pytest.fixture(scope="session")
