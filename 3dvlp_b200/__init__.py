@@ -15,7 +15,7 @@ Public surface = the reference's (file:line in each module docstring):
 import sys as _sys
 
 from . import _lib  # noqa: F401
-from ._lib import get_option, set_option  # noqa: F401
+from ._lib import get_option, get_stat, set_option, set_option_thread, thread_options  # noqa: F401
 from . import _ext, backbone, nn_distance as _nn_distance_mod, pointnet2_modules, pointnet2_utils, pytorch_utils, voting, loss_detection, box_util, loss_grounding, contrast, proposal  # noqa: F401
 from .backbone import Pointnet2Backbone  # noqa: F401
 from .graph import GraphedBackbone  # noqa: F401

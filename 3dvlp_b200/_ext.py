@@ -21,7 +21,7 @@ def furthest_point_sampling(points, nsamples):
     L.check_contiguous(points, "points"); L.check_float(points, "points")
     L.require_cuda_path(points)
     b, n = points.size(0), points.size(1)
-    out = torch.zeros(b, nsamples, device=points.device, dtype=torch.int32)
+    out = torch.empty(b, nsamples, device=points.device, dtype=torch.int32)  # every index is written
     L.call("pn2_furthest_point_sampling", b, n, int(nsamples), L.ptr(points), None, L.ptr(out),
            L.stream_of(points), device=points.device)
     return out
@@ -34,7 +34,7 @@ def furthest_point_sampling_gather(points, nsamples, ordered=False):
     L.check_contiguous(points, "points"); L.check_float(points, "points")
     L.require_cuda_path(points)
     b, n = points.size(0), points.size(1)
-    out = torch.zeros(b, nsamples, device=points.device, dtype=torch.int32)
+    out = torch.empty(b, nsamples, device=points.device, dtype=torch.int32)  # every index is written
     new_xyz = torch.empty(b, nsamples, 3, device=points.device, dtype=torch.float32)
     L.call("pn2_furthest_point_sampling_gather_ordered" if ordered else "pn2_furthest_point_sampling_gather",
            b, n, int(nsamples), L.ptr(points), L.ptr(out),
@@ -74,7 +74,9 @@ def ball_query(new_xyz, xyz, radius, nsample):
     L.require_cuda_path(new_xyz); L.check_cuda(xyz, "xyz")
     b, m = new_xyz.size(0), new_xyz.size(1)
     n = xyz.size(1)
-    idx = torch.zeros(b, m, nsample, device=new_xyz.device, dtype=torch.int32)
+    # the reference relies on torch::zeros for empty balls (ball_query.cpp:24-26); pn2_ball_query writes
+    # those zeros itself (include/pointnet2_b200.h), so no fill kernel runs ahead of it
+    idx = torch.empty(b, m, nsample, device=new_xyz.device, dtype=torch.int32)
     L.call("pn2_ball_query", b, n, m, _f(radius), int(nsample), L.ptr(new_xyz), L.ptr(xyz), L.ptr(idx),
            L.stream_of(new_xyz), device=new_xyz.device)
     return idx

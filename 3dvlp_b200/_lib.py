@@ -29,6 +29,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.pn2_last_error.restype = ctypes.c_char_p
         L.pn2_abi_version.restype = ctypes.c_int
+        L.pn2_get_stat.restype = ctypes.c_longlong
         _lib = L
     return _lib
 
@@ -88,6 +89,40 @@ def set_option(name, value):
 
 def get_option(name):
     return int(lib().pn2_get_option(name.encode()))
+
+
+def set_option_thread(name, value):
+    """pn2_set_option_thread: override an option for calls made by THIS host thread only
+    (value=None or < 0 removes the override)."""
+    L = lib()
+    if L.pn2_set_option_thread(name.encode(), -1 if value is None else int(value)) != 0:
+        raise Pn2Error(L.pn2_last_error().decode())
+
+
+class thread_options:
+    """``with thread_options(fps_bucket=1, sa_tiles_per_group=16): ...`` -- per-thread option overrides
+    for the duration of the block; other host threads keep launching what the process-wide options say."""
+
+    def __init__(self, **opts):
+        self.opts = opts
+
+    def __enter__(self):
+        for k, v in self.opts.items():
+            set_option_thread(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k in self.opts:
+            set_option_thread(k, None)
+        return False
+
+
+def get_stat(name):
+    """pn2_get_stat: how often a kernel variant was launched by this process (e.g. "fps_bucket_launches")."""
+    v = int(lib().pn2_get_stat(name.encode()))
+    if v < 0:
+        raise Pn2Error("unknown statistic %r" % name)
+    return v
 
 
 # ---- argument checks with the reference's messages (include/utils.h:10-30) -----------------------

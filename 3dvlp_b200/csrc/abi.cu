@@ -2,9 +2,14 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace pn2 {
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 static thread_local char g_err[512] = "";
 
@@ -24,37 +29,65 @@ int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-  if (!cached[dev]) {
-    int v = 0;
+  int v = __atomic_load_n(&cached[dev], __ATOMIC_RELAXED);  // racing threads store the same value
+  if (!v) {
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-    cached[dev] = v;
+    __atomic_store_n(&cached[dev], v, __ATOMIC_RELAXED);
   }
-  return cached[dev];
+  return v;
+}
+
+void keep_workspace_pool() {
+  static int ready[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  if (__atomic_load_n(&ready[dev], __ATOMIC_ACQUIRE)) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);  // idempotent
+  }
+  __atomic_store_n(&ready[dev], 1, __ATOMIC_RELEASE);
 }
 
 // One int per device, set by a kernel whose bounded mbarrier wait timed out (a protocol bug must
 // surface as an error, never as a hung GPU).  Polled by pn2_poll_device_error().
 static int* g_err_flag[64] = {nullptr};
 
+// Entry points are called from several host threads (DataParallel workers, the autograd engine): the
+// first caller per device publishes the flag with a compare-and-swap, a loser frees its allocation.
 int* device_err_flag() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (!g_err_flag[dev]) {
-    int* p = nullptr;
-    if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(p, 0, sizeof(int));
-    g_err_flag[dev] = p;
-  }
-  return g_err_flag[dev];
+  int* cur = __atomic_load_n(&g_err_flag[dev], __ATOMIC_ACQUIRE);
+  if (cur) return cur;
+  int* p = nullptr;
+  if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
+  if (cudaMemset(p, 0, sizeof(int)) != cudaSuccess) { cudaFree(p); return nullptr; }
+  int* expected = nullptr;
+  if (__atomic_compare_exchange_n(&g_err_flag[dev], &expected, p, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) return p;
+  cudaFree(p);
+  return expected;
 }
+
+// ---- host-side statistics (pn2_get_stat): which kernel variant a call really launched ------------
+static const char* const kStatName[STAT_COUNT] = {"fps_cluster_launches", "fps_bucket_launches", "fps_pair_launches",
+                                                   "bq_grid_launches", "bq_small_grid_launches", "bq_scan_launches",
+                                                   "nn_small_launches", "nn_tiled_launches"};
+static long long g_stat[STAT_COUNT] = {0};
+void stat_add(Stat s, long long v) { __atomic_fetch_add(&g_stat[s], v, __ATOMIC_RELAXED); }
 
 // ---- run-time options ----------------------------------------------------------------------------
 static const char* const kOptName[OPT_COUNT] = {"fps_bucket", "bq_grid", "sa_tiles_per_group"};
 static const char* const kOptEnv[OPT_COUNT] = {"PN2_FPS_BUCKET", "PN2_BQ_GRID", "PN2_SA_TILES_PER_GROUP"};
 static const int kOptDefault[OPT_COUNT] = {0, 1, 0};
 static int g_opt[OPT_COUNT] = {-1, -1, -1};
+// per-thread override (pn2_set_option_thread): -1 = follow the process-wide value.  A host thread that
+// captures a CUDA graph with other settings does not disturb calls made by other threads meanwhile.
+static thread_local int t_opt[OPT_COUNT] = {-1, -1, -1};
 
 int option_value(Option o) {
+  if (t_opt[o] >= 0) return t_opt[o];
   int v = __atomic_load_n(&g_opt[o], __ATOMIC_RELAXED);
   if (v < 0) {
     const char* e = getenv(kOptEnv[o]);
@@ -78,6 +111,23 @@ extern "C" int pn2_set_option(const char* name, int value) {
   return PN2_ERR_INVALID;
 }
 
+extern "C" int pn2_set_option_thread(const char* name, int value) {
+  for (int i = 0; i < pn2::OPT_COUNT; ++i) {
+    if (name && strcmp(name, pn2::kOptName[i]) == 0) {
+      pn2::t_opt[i] = value < 0 ? -1 : value;
+      return PN2_OK;
+    }
+  }
+  pn2::set_error("set_option_thread: unknown option '%s'", name ? name : "(null)");
+  return PN2_ERR_INVALID;
+}
+
+extern "C" long long pn2_get_stat(const char* name) {
+  for (int i = 0; i < pn2::STAT_COUNT; ++i)
+    if (name && strcmp(name, pn2::kStatName[i]) == 0) return __atomic_load_n(&pn2::g_stat[i], __ATOMIC_RELAXED);
+  return -1;
+}
+
 extern "C" int pn2_get_option(const char* name) {
   for (int i = 0; i < pn2::OPT_COUNT; ++i)
     if (name && strcmp(name, pn2::kOptName[i]) == 0) return pn2::option_value(static_cast<pn2::Option>(i));
@@ -85,6 +135,7 @@ extern "C" int pn2_get_option(const char* name) {
 }
 
 extern "C" int pn2_poll_device_error(int* flag_out, void* stream) {
+  PN2_RANGE("pn2_poll_device_error");
   int* p = pn2::device_err_flag();
   if (!p) { pn2::set_error("poll_device_error: no flag"); return PN2_ERR_CUDA; }
   int v = 0;

@@ -353,19 +353,7 @@ int ball_query_grid(int b, int n, int m, float radius, int nsample, const float*
   const size_t cursor_bytes = static_cast<size_t>(b) * T * sizeof(int);
   const size_t sorted_off = (start_bytes + cursor_bytes + 255) & ~static_cast<size_t>(255);
   const size_t bytes = sorted_off + static_cast<size_t>(b) * n * sizeof(float4);
-  // keep freed workspace cached in the device's default pool (the default threshold of 0 hands the
-  // memory back to the driver at every synchronisation and makes the next call pay for a real malloc)
-  static bool pool_ready[64] = {false};
-  int dev = 0;
-  PN2_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    pool_ready[dev] = true;
-  }
+  keep_workspace_pool();  // abi.cu: freed workspace stays cached in the device's default pool
   uint8_t* ws = nullptr;
   PN2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), bytes, s));
   int* start = reinterpret_cast<int*>(ws);

@@ -177,6 +177,7 @@ using namespace pn2;
 extern "C" int pn2_box3d_diou_pairs(int b, int l, int k, const float* center1, const float* size1,
                                     const float* center2, const float* size2, float* iou, float* diou,
                                     void* stream) {
+  PN2_RANGE("pn2_box3d_diou_pairs");
   if (b <= 0 || l <= 0 || k <= 0) return PN2_OK;
   PN2_REQUIRE(center1 && size1 && center2 && size2 && (iou || diou), "box3d_diou_pairs: bad arguments");
   const long long total = static_cast<long long>(b) * l * k;
@@ -190,6 +191,7 @@ extern "C" int pn2_box3d_diou_pairs_grad(int b, int l, int k, const float* cente
                                          const float* center2, const float* size2, const float* grad_iou,
                                          const float* grad_diou, float* grad_center1, float* grad_size1,
                                          void* stream) {
+  PN2_RANGE("pn2_box3d_diou_pairs_grad");
   if (b <= 0 || k <= 0) return PN2_OK;
   PN2_REQUIRE(l >= 0 && center1 && size1 && (l == 0 || (center2 && size2)) && grad_center1 && grad_size1,
               "box3d_diou_pairs_grad: bad arguments");
@@ -204,6 +206,7 @@ extern "C" int pn2_box3d_diou_grad(long long p, const float* center1, const floa
                                    const float* size2, const float* grad_iou, const float* grad_diou,
                                    float* grad_center1, float* grad_size1, float* grad_center2,
                                    float* grad_size2, void* stream) {
+  PN2_RANGE("pn2_box3d_diou_grad");
   if (p <= 0) return PN2_OK;
   PN2_REQUIRE(center1 && size1 && center2 && size2, "box3d_diou_grad: bad arguments");
   diou_elementwise_grad_kernel<<<static_cast<unsigned>((p + 255) / 256), 256, 0, as_stream(stream)>>>(

@@ -49,10 +49,28 @@ inline int opt_n_threads(int work_size) {
 }
 
 int sm_count();
+// Raise the release threshold of the current device's default memory pool once (thread-safe): the
+// default of 0 hands freed workspace back to the driver at every synchronisation, so the next
+// cudaMallocAsync would pay for a real allocation.
+void keep_workspace_pool();
 
 // run-time options (pn2_set_option); initial values come from the environment
 enum Option { OPT_FPS_BUCKET = 0, OPT_BQ_GRID = 1, OPT_SA_TILES_PER_GROUP = 2, OPT_COUNT = 3 };
 int option_value(Option o);
+
+// host-side launch statistics, read back with pn2_get_stat(name): the parity tests assert through them
+// that the kernel variant they mean to cover is the one that ran
+enum Stat { STAT_FPS_CLUSTER = 0, STAT_FPS_BUCKET, STAT_FPS_PAIR, STAT_BQ_GRID, STAT_BQ_SMALL_GRID, STAT_BQ_SCAN,
+            STAT_NN_SMALL, STAT_NN_TILED, STAT_COUNT };
+void stat_add(Stat s, long long v = 1);
+
+// NVTX range around every C-ABI entry point (header-only NVTX3: the tools library is looked up at run
+// time, there is no link dependency and no cost when no tool is attached)
+struct NvtxRange {
+  explicit NvtxRange(const char* name);
+  ~NvtxRange();
+};
+#define PN2_RANGE(name) ::pn2::NvtxRange _pn2_range(name)
 
 // ---- device helpers -------------------------------------------------------------------------
 

@@ -195,6 +195,7 @@ using namespace pn2;
 extern "C" int pn2_fp_prepare(int b, int n, int m, int c1, int c2, int kpad, const float* unknown,
                               const float* known, const float* unknow_feats, const float* known_feats,
                               void* out_bf16, void* stream) {
+  PN2_RANGE("pn2_fp_prepare");
   if (b <= 0 || n <= 0) return PN2_OK;
   PN2_REQUIRE(m > 0 && c2 > 0 && c1 >= 0 && kpad >= c1 + c2 && kpad % 64 == 0, "fp_prepare: bad sizes");
   PN2_REQUIRE(unknown && known && known_feats && out_bf16 && (c1 == 0 || unknow_feats) && b <= 65535,
@@ -209,6 +210,7 @@ extern "C" int pn2_fp_prepare(int b, int n, int m, int c1, int c2, int kpad, con
 
 extern "C" int pn2_three_nn_weights(int b, int n, int m, const float* unknown, const float* known, int* idx,
                                     float* weight, void* stream) {
+  PN2_RANGE("pn2_three_nn_weights");
   if (b <= 0 || n <= 0) return PN2_OK;
   PN2_REQUIRE(m > 0 && unknown && known && idx && weight && b <= 65535, "three_nn_weights: bad arguments");
   dim3 grid((n + 7) / 8, b);
@@ -220,6 +222,7 @@ extern "C" int pn2_three_nn_weights(int b, int n, int m, const float* unknown, c
 extern "C" int pn2_fp_prepare_indexed(int b, int n, int m, int c1, int c2, int kpad, const int* idx,
                                       const float* weight, const float* unknow_feats, const float* known_feats,
                                       void* out_bf16, void* stream) {
+  PN2_RANGE("pn2_fp_prepare_indexed");
   if (b <= 0 || n <= 0) return PN2_OK;
   PN2_REQUIRE(m > 0 && c2 > 0 && c1 >= 0 && kpad >= c1 + c2 && kpad % 64 == 0, "fp_prepare_indexed: bad sizes");
   PN2_REQUIRE(idx && weight && known_feats && out_bf16 && (c1 == 0 || unknow_feats) && b <= 65535,

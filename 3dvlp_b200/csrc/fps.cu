@@ -458,8 +458,10 @@ int fps_run(int b, int n, int m, const float* dataset, int* idxs, float* new_xyz
   //   bucketed kernel           1 SM per scene with spatial pruning: ~2x the latency but 1/16 of the
   //                             SM footprint, the right choice when several batches are in flight.
   // Selected with pn2_set_option("fps_bucket", 0|1) (initial value: env PN2_FPS_BUCKET, default 0).
-  if (option_value(OPT_FPS_BUCKET) && fps_bucket_supported(n))
+  if (option_value(OPT_FPS_BUCKET) && fps_bucket_supported(n)) {
+    stat_add(STAT_FPS_BUCKET);
     return fps_bucket_run(b, n, m, log2bs, dataset, idxs, new_xyz, stream);
+  }
 
   static const int force_cluster = env_int("PN2_FPS_CLUSTER", 0);
   static const int force_threads = env_int("PN2_FPS_THREADS", 0);
@@ -488,17 +490,20 @@ int fps_run(int b, int n, int m, const float* dataset, int* idxs, float* new_xyz
     cluster = 8;
     for (int cs = 16; cs >= 8; cs -= 2) {
       if (a.rows > cs * (threads / bs) * 16) continue;  // would not fit the register budget
-      if (!active_cache[cs]) {
+      int cached = __atomic_load_n(&active_cache[cs], __ATOMIC_RELAXED);  // idempotent: racing threads store the same value
+      if (!cached) {
         int act = 0;
         if (run_cfg(cs, threads, a, bs, b, stream, &act) != PN2_OK || act <= 0) act = -1;
-        active_cache[cs] = act;
+        __atomic_store_n(&active_cache[cs], act, __ATOMIC_RELAXED);
+        cached = act;
       }
-      if (active_cache[cs] >= b) { cluster = cs; break; }
+      if (cached >= b) { cluster = cs; break; }
     }
     if (a.rows > cluster * (threads / bs) * 16) { cluster = 16; threads = 1024; }
   }
   PN2_REQUIRE(cluster >= 1 && cluster <= MAXC && (threads == 512 || threads == 1024),
               "furthest_point_sampling: unsupported cluster=%d threads=%d", cluster, threads);
+  stat_add(STAT_FPS_CLUSTER);
   return run_cfg(cluster, threads, a, bs, b, stream, nullptr);
 }
 
@@ -515,16 +520,19 @@ extern "C" int pn2_fps_timing(long long* out7) {
 
 extern "C" int pn2_furthest_point_sampling(int b, int n, int m, const float* dataset, float* temp,
                                            int* idxs, void* stream) {
+  PN2_RANGE("pn2_furthest_point_sampling");
   (void)temp;  // running minima stay in registers; the reference's scratch is not needed
   return pn2::fps_run(b, n, m, dataset, idxs, nullptr, pn2::as_stream(stream));
 }
 
 extern "C" int pn2_furthest_point_sampling_gather(int b, int n, int m, const float* dataset, int* idxs,
                                                   float* new_xyz, void* stream) {
+  PN2_RANGE("pn2_furthest_point_sampling_gather");
   return pn2::fps_run(b, n, m, dataset, idxs, new_xyz, pn2::as_stream(stream));
 }
 
 extern "C" int pn2_furthest_point_sampling_gather_ordered(int b, int n, int m, const float* dataset, int* idxs,
                                                           float* new_xyz, void* stream) {
+  PN2_RANGE("pn2_furthest_point_sampling_gather_ordered");
   return pn2::fps_run(b, n, m, dataset, idxs, new_xyz, pn2::as_stream(stream), true);
 }

@@ -390,6 +390,7 @@ static int launch_interp_grad(int b, int c, int n, int m, const float* grad_out,
 
 extern "C" int pn2_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx,
                                  float* out, void* stream) {
+  PN2_RANGE("pn2_gather_points");
   if (b <= 0 || c <= 0 || npoints <= 0) return PN2_OK;
   PN2_REQUIRE(points && idx && out && n > 0 && b <= 65535, "gather_points: bad arguments");
   return launch_gather("gather_points", b, c, n, npoints, points, idx, out, as_stream(stream));
@@ -397,6 +398,7 @@ extern "C" int pn2_gather_points(int b, int c, int n, int npoints, const float* 
 
 extern "C" int pn2_gather_points_grad(int b, int c, int n, int npoints, const float* grad_out,
                                       const int* idx, float* grad_points, void* stream) {
+  PN2_RANGE("pn2_gather_points_grad");
   if (b <= 0 || c <= 0 || npoints <= 0) return PN2_OK;
   PN2_REQUIRE(grad_out && idx && grad_points && n > 0 && b <= 65535, "gather_points_grad: bad arguments");
   return launch_scatter("gather_points_grad", b, c, n, npoints, grad_out, idx, grad_points, as_stream(stream));
@@ -404,6 +406,7 @@ extern "C" int pn2_gather_points_grad(int b, int c, int n, int npoints, const fl
 
 extern "C" int pn2_group_points(int b, int c, int n, int npoints, int nsample, const float* points,
                                 const int* idx, float* out, void* stream) {
+  PN2_RANGE("pn2_group_points");
   if (b <= 0 || c <= 0 || npoints <= 0 || nsample <= 0) return PN2_OK;
   PN2_REQUIRE(points && idx && out && n > 0 && b <= 65535, "group_points: bad arguments");
   const long long q = static_cast<long long>(npoints) * nsample;
@@ -412,6 +415,7 @@ extern "C" int pn2_group_points(int b, int c, int n, int npoints, int nsample, c
 
 extern "C" int pn2_group_points_grad(int b, int c, int n, int npoints, int nsample, const float* grad_out,
                                      const int* idx, float* grad_points, void* stream) {
+  PN2_RANGE("pn2_group_points_grad");
   if (b <= 0 || c <= 0 || npoints <= 0 || nsample <= 0) return PN2_OK;
   PN2_REQUIRE(grad_out && idx && grad_points && n > 0 && b <= 65535, "group_points_grad: bad arguments");
   const long long q = static_cast<long long>(npoints) * nsample;
@@ -420,6 +424,7 @@ extern "C" int pn2_group_points_grad(int b, int c, int n, int npoints, int nsamp
 
 extern "C" int pn2_three_interpolate(int b, int c, int m, int n, const float* points, const int* idx,
                                      const float* weight, float* out, void* stream) {
+  PN2_RANGE("pn2_three_interpolate");
   if (b <= 0 || c <= 0 || n <= 0) return PN2_OK;
   PN2_REQUIRE(points && idx && weight && out && m > 0 && b <= 65535, "three_interpolate: bad arguments");
   switch (n >= 2 * m ? interp_tile_channels(c, m, 4) : 0) {
@@ -436,6 +441,7 @@ extern "C" int pn2_three_interpolate(int b, int c, int m, int n, const float* po
 
 extern "C" int pn2_three_interpolate_grad(int b, int c, int n, int m, const float* grad_out, const int* idx,
                                           const float* weight, float* grad_points, void* stream) {
+  PN2_RANGE("pn2_three_interpolate_grad");
   if (b <= 0 || c <= 0 || n <= 0) return PN2_OK;
   PN2_REQUIRE(grad_out && idx && weight && grad_points && m > 0 && b <= 65535,
               "three_interpolate_grad: bad arguments");

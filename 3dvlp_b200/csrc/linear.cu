@@ -231,6 +231,7 @@ int* device_err_flag();  // defined in abi.cu
 using namespace pn2;
 
 extern "C" int pn2_pack_weight_bf16(int n, int k, int kpad, const float* w, void* out, void* stream) {
+  PN2_RANGE("pn2_pack_weight_bf16");
   PN2_REQUIRE(n > 0 && k > 0 && kpad >= k && kpad % 64 == 0 && w && out, "pack_weight_bf16: bad arguments");
   const int total = n * (kpad / 8);
   pack_weight_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(n, k, kpad, w, static_cast<uint8_t*>(out));
@@ -239,6 +240,7 @@ extern "C" int pn2_pack_weight_bf16(int n, int k, int kpad, const float* w, void
 }
 
 extern "C" int pn2_pack_rows_bf16(int b, int c, int n, int kpad, const float* features, void* out, void* stream) {
+  PN2_RANGE("pn2_pack_rows_bf16");
   PN2_REQUIRE(b > 0 && c > 0 && n > 0 && kpad >= c && features && out && b <= 65535, "pack_rows_bf16: bad arguments");
   if (kpad % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     dim3 grid((n + 31) / 32, (kpad + 63) / 64, b);
@@ -253,6 +255,7 @@ extern "C" int pn2_pack_rows_bf16(int b, int c, int n, int kpad, const float* fe
 
 extern "C" int pn2_pack_point_rows_bf16(long long rows, int ld, int col0, int c, int kpad, const float* in, void* out,
                                         void* stream) {
+  PN2_RANGE("pn2_pack_point_rows_bf16");
   if (rows <= 0) return PN2_OK;
   PN2_REQUIRE(c > 0 && col0 >= 0 && ld >= col0 + c && kpad >= c && kpad % 8 == 0 && in && out,
               "pack_point_rows_bf16: bad arguments");
@@ -265,6 +268,7 @@ extern "C" int pn2_pack_point_rows_bf16(long long rows, int ld, int col0, int c,
 
 extern "C" int pn2_linear_bf16(int m, int n, int k, const void* x_bf16, const void* w_packed, const float* bias,
                                int relu, int out_mode, int rows_per_batch, void* y, void* stream) {
+  PN2_RANGE("pn2_linear_bf16");
   if (m <= 0) return PN2_OK;
   PN2_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0, "linear_bf16: n=%d must be a multiple of 16 in [16,256]", n);
   PN2_REQUIRE(k >= 64 && k % 64 == 0, "linear_bf16: k=%d must be a positive multiple of 64", k);

@@ -52,7 +52,7 @@ struct SaArgs {
   const float* b3;
   float* out_cm;         // (B, C3, npoint) fp32
   int* err;
-  int* tile_counter;     // {next tile, finished CTAs}, both zero at launch: tiles are handed out dynamically
+  int* tile_counter;     // next tile, zeroed by sa_count_kernel: tiles are handed out dynamically
   const int* row_src;    // (B, cap) compacted rows: index into idx (centre * ns + slot) or -1; see sa_plan_kernel
   const int* tiles_b;    // (B) tiles of each scene's compacted row list
   int cap;               // row capacity of a scene's region: npoint * ns rounded up to 128
@@ -476,16 +476,6 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   if (!weights_ready && threadIdx.x == 0) mbar_wait(&bar_w, 0);
   tc::fence_before_sync();
   __syncthreads();
-  // the last CTA to finish re-arms the counter pair for the next launch that uses this slot (no memset
-  // node per launch: with a dozen graphs in flight those serialise on the copy engine)
-  if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(a.tile_counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
-      a.tile_counter[0] = 0;
-      a.tile_counter[1] = 0;
-      __threadfence();
-    }
-  }
   if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, tmem_cols);
 }
 
@@ -504,8 +494,9 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
 // distinct hits of every centre (warp per centre, all scenes at once) + zero-fill of out_cm
 __global__ void __launch_bounds__(256)
 sa_count_kernel(int n_centres, int ns, const int* __restrict__ idx, int* __restrict__ cnt_out,
-                float4* __restrict__ out4, long long n_out4) {
+                float4* __restrict__ out4, long long n_out4, int* __restrict__ tile_counter) {
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *tile_counter = 0;
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n_out4; i += static_cast<long long>(gridDim.x) * 256)
     out4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -601,48 +592,6 @@ int launch_cd(int cd, const SaArgs& a, int grid, size_t smem, cudaStream_t s) {
   return PN2_OK;
 }
 
-// One zeroed {next tile, finished CTAs} pair per launch.  Eager launches rotate through a per-device ring
-// (4096 launches would have to be in flight to collide).  A launch that is being captured into a CUDA
-// graph gets a slot of its own that is never handed out again: the graph replays with that address
-// for as long as it lives, possibly concurrently with eager work and with other graphs.
-constexpr int kCounterSlots = 4096;
-constexpr int kCaptureSlots = 1 << 16;  // captured launches per device over the life of the process
-int* g_counters[64] = {nullptr};
-unsigned g_counter_next = 0;
-int* g_capture_chunk[64] = {nullptr};
-int g_capture_used[64] = {0};
-int g_capture_lock = 0;
-
-int* next_tile_counter(cudaStream_t stream) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) return nullptr;
-  if (cap != cudaStreamCaptureStatusNone) {
-    // the chunk was allocated by an earlier eager call (GraphedBackbone warms up before it captures);
-    // allocating here would be an illegal call inside a global-mode capture
-    while (__atomic_exchange_n(&g_capture_lock, 1, __ATOMIC_ACQUIRE)) {}
-    int* slot = nullptr;
-    if (g_capture_chunk[dev] && g_capture_used[dev] < kCaptureSlots) slot = g_capture_chunk[dev] + 2 * g_capture_used[dev]++;
-    __atomic_store_n(&g_capture_lock, 0, __ATOMIC_RELEASE);
-    return slot;
-  }
-  if (!__atomic_load_n(&g_counters[dev], __ATOMIC_ACQUIRE)) {
-    int* p = nullptr;
-    const size_t bytes = 2 * static_cast<size_t>(kCounterSlots + kCaptureSlots) * sizeof(int);
-    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
-    if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaFree(p); return nullptr; }  // kernels re-arm their slot
-    int* expected = nullptr;
-    if (!__atomic_compare_exchange_n(&g_counters[dev], &expected, p, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
-      cudaFree(p);
-    } else {
-      g_capture_chunk[dev] = p + 2 * kCounterSlots;
-    }
-  }
-  const unsigned slot = __atomic_fetch_add(&g_counter_next, 1u, __ATOMIC_RELAXED) % kCounterSlots;
-  return g_counters[dev] + 2 * slot;
-}
-
 }  // namespace
 
 int* device_err_flag();
@@ -656,6 +605,7 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
                                 const float* g, int c1, int c2, int c3, const float* w1, const float* b1,
                                 const void* w2_packed, const float* b2, const void* w3_packed, const float* b3,
                                 float* out_cm, void* out_pm_bf16, void* stream) {
+  PN2_RANGE("pn2_sa_group_mlp");
   if (b <= 0 || npoint <= 0) return PN2_OK;
   PN2_REQUIRE(nsample == 16 || nsample == 32 || nsample == 64 || nsample == 128,
               "sa_group_mlp: nsample=%d must be 16, 32, 64 or 128", nsample);
@@ -677,39 +627,27 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
   a.total_rows = static_cast<long long>(b) * npoint * nsample;
   a.err = device_err_flag();
   PN2_REQUIRE(a.err != nullptr, "sa_group_mlp: cannot allocate the device error flag");
-  a.tile_counter = next_tile_counter(as_stream(stream));
-  PN2_REQUIRE(a.tile_counter != nullptr,
-              "sa_group_mlp: no tile counter (run the op once eagerly before capturing it into a CUDA graph)");
   // ---- row plan (stream-ordered workspace: the call stays asynchronous and capturable) -----------------
   PN2_REQUIRE(b <= kMaxScenes, "sa_group_mlp: at most %d scenes per call (got %d)", kMaxScenes, b);
   PN2_REQUIRE(npoint <= 4096, "sa_group_mlp: npoint=%d exceeds the row plan's 4096", npoint);
   PN2_REQUIRE(static_cast<long long>(b) * npoint * nsample < (1LL << 31), "sa_group_mlp: b * npoint * nsample must stay below 2^31");
   const int cap = (npoint * nsample + 127) & ~127;
   const size_t plan_smem = (static_cast<size_t>(npoint) + 40) * sizeof(int);
-  {  // keep freed workspace in the stream-ordered pool instead of returning it to the OS at every sync
-    static bool pool_ready[64] = {false};
-    int dev = 0;
-    PN2_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
-      pool_ready[dev] = true;
-    }
-  }
+  keep_workspace_pool();
   int* ws = nullptr;
   const size_t n_centres = static_cast<size_t>(b) * npoint;
-  PN2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (static_cast<size_t>(b) * cap + b + n_centres) * sizeof(int),
+  PN2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (static_cast<size_t>(b) * cap + b + n_centres + 2) * sizeof(int),
                            as_stream(stream)));
   int* tiles_b = ws + static_cast<size_t>(b) * cap;
   int* cnt_ws = tiles_b + b;
+  // the dynamic tile counter lives in the call's own workspace and is zeroed by sa_count_kernel: no
+  // process-wide ring, nothing to recycle when a captured graph is destroyed
+  a.tile_counter = cnt_ws + n_centres;
   a.row_src = ws; a.tiles_b = tiles_b; a.cap = cap;
   {
     const long long n_out4 = (static_cast<long long>(b) * c3 * npoint) >> 2;  // c3 is a multiple of 128
     sa_count_kernel<<<static_cast<unsigned>((n_centres + 7) / 8), 256, 0, as_stream(stream)>>>(
-        static_cast<int>(n_centres), nsample, idx, cnt_ws, reinterpret_cast<float4*>(out_cm), n_out4);
+        static_cast<int>(n_centres), nsample, idx, cnt_ws, reinterpret_cast<float4*>(out_cm), n_out4, a.tile_counter);
     sa_plan_kernel<<<b, 1024, plan_smem, as_stream(stream)>>>(npoint, a.ns_shift, cap, cnt_ws, ws, tiles_b);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { cudaFreeAsync(ws, as_stream(stream)); return cuda_fail(e, "sa_plan_kernel"); }

@@ -150,6 +150,7 @@ bool ball_query_small_supported(int n);
 
 extern "C" int pn2_ball_query(int b, int n, int m, float radius, int nsample, const float* new_xyz,
                               const float* xyz, int* idx, void* stream) {
+  PN2_RANGE("pn2_ball_query");
   using namespace pn2;
   if (b <= 0 || m <= 0 || nsample <= 0) return PN2_OK;
   PN2_REQUIRE(n >= 0 && new_xyz && idx && (xyz || n == 0), "ball_query: bad arguments");
@@ -157,13 +158,18 @@ extern "C" int pn2_ball_query(int b, int n, int m, float radius, int nsample, co
   const float radius2 = radius * radius;  // fp32 product, ball_query_gpu.cu:27
   // large clouds: hashed-grid search (identical output, ~100x fewer distance tests);
   // pn2_set_option("bq_grid", 0) / PN2_BQ_GRID=0 forces the linear scan
-  if (option_value(OPT_BQ_GRID) && n >= 4096 && radius2 > 0.f && std::isfinite(radius) && fabsf(radius) > 1e-6f)
+  if (option_value(OPT_BQ_GRID) && n >= 4096 && radius2 > 0.f && std::isfinite(radius) && fabsf(radius) > 1e-6f) {
+    stat_add(STAT_BQ_GRID);
     return ball_query_grid(b, n, m, radius, nsample, new_xyz, xyz, idx, as_stream(stream));
+  }
   // mid-sized clouds (SA2): the same search out of a grid built in shared memory, one launch; a centre
   // whose stencil would hold more than n/8 candidates scans linearly inside that kernel
   if (option_value(OPT_BQ_GRID) && ball_query_small_supported(n) && radius2 > 0.f && std::isfinite(radius) &&
-      fabsf(radius) > 1e-6f)
+      fabsf(radius) > 1e-6f) {
+    stat_add(STAT_BQ_SMALL_GRID);
     return ball_query_small(b, n, m, radius, nsample, new_xyz, xyz, idx, as_stream(stream));
+  }
+  stat_add(STAT_BQ_SCAN);
   const int per_cta = BQ_CPW * BQ_WARPS;
   dim3 grid((m + per_cta - 1) / per_cta, b);
   ball_query_kernel<<<grid, BQ_WARPS * 32, 0, as_stream(stream)>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
@@ -173,6 +179,7 @@ extern "C" int pn2_ball_query(int b, int n, int m, float radius, int nsample, co
 
 extern "C" int pn2_three_nn(int b, int n, int m, const float* unknown, const float* known, float* dist2,
                             int* idx, void* stream) {
+  PN2_RANGE("pn2_three_nn");
   using namespace pn2;
   if (b <= 0 || n <= 0) return PN2_OK;
   PN2_REQUIRE(m >= 0 && unknown && dist2 && idx && (known || m == 0), "three_nn: bad arguments");

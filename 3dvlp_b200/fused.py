@@ -130,7 +130,7 @@ def sa_features(module, plan, xyz, features, new_xyz, rows=None, idx=None):
             feat = features.contiguous().float()
     else:
         if rows is None:
-            rows = getattr(features, "_pn2_rows", None)
+            rows = cached_rows(features)
         if rows is None or rows.shape != (b * n, plan.w1f.kpad) or rows.device != dev:
             rows = tcm.pack_rows(features.contiguous().float(), plan.w1f.kpad)
         g = tcm.linear(rows, plan.w1f, None, relu=False, out="f32")
@@ -141,8 +141,22 @@ def sa_features(module, plan, xyz, features, new_xyz, rows=None, idx=None):
            L.ptr(new_xyz), L.ptr(idx), plan.c_in if plan.direct else 0, L.ptr(feat), L.ptr(g), plan.c1, plan.c2,
            plan.c3, L.ptr(plan.w1), L.ptr(plan.b1), L.ptr(plan.w2p.data), L.ptr(plan.b2), L.ptr(plan.w3p.data),
            L.ptr(plan.b3), L.ptr(out_cm), L.ptr(out_pm), L.stream_of(xyz), device=dev)
-    out_cm._pn2_rows = out_pm  # bf16 point-major twin: the next SA layer's GEMM operand, no repack
+    attach_rows(out_cm, out_pm)  # bf16 point-major twin: the next SA layer's GEMM operand, no repack
     return out_cm
+
+
+def attach_rows(features, rows):
+    """Remember the bf16 point-major twin of `features` together with the tensor version it was made
+    from: an in-place edit of the fp32 tensor (mul_, masking, copy_) invalidates the twin."""
+    features._pn2_rows = (features._version, rows)
+
+
+def cached_rows(features):
+    """The twin attached by attach_rows, or None when there is none or `features` has changed since."""
+    rec = getattr(features, "_pn2_rows", None)
+    if rec is None or rec[0] != features._version:
+        return None
+    return rec[1]
 
 
 def sa_forward(module, xyz, features, inds):

@@ -26,14 +26,15 @@ class GraphedBackbone:
         self.backbone = backbone
         # throughput=True captures the single-SM bucketed FPS (meant for several graphs in flight on
         # separate streams); the default captures the low-latency 16-SM cluster FPS
+        # The options are set as PER-THREAD overrides (pn2_set_option_thread): a concurrent eager call on
+        # another host thread keeps launching what the process-wide options say.
         from . import _lib
-        prev = _lib.get_option("fps_bucket")
-        prev_k = _lib.get_option("sa_tiles_per_group")
-        _lib.set_option("fps_bucket", 1 if throughput else 0)
         # throughput=True also launches the fused SA bodies on fewer persistent CTAs (>= 16 tiles per
         # group): their per-CTA prologue is SM-time that other batches in flight could use
-        _lib.set_option("sa_tiles_per_group", (prev_k or 16) if throughput else 0)
-        try:
+        opts = dict(fps_bucket=1, sa_tiles_per_group=_lib.get_option("sa_tiles_per_group") or 16) if throughput \
+            else dict(fps_bucket=0, sa_tiles_per_group=0)
+        self.options = opts
+        with _lib.thread_options(**opts):
             self.static_in = example_batch.clone().contiguous()
             self.graph = None
             self.static_out = None
@@ -54,14 +55,21 @@ class GraphedBackbone:
             except Exception as ex:  # pragma: no cover - depends on driver behaviour
                 self.capture_error = repr(ex)
                 torch.cuda.synchronize(self.static_in.device)
-        finally:
-            _lib.set_option("fps_bucket", prev)
-            _lib.set_option("sa_tiles_per_group", prev_k)
+
+    def check(self):
+        """Synchronise and raise Pn2Error if a kernel of this device bailed out of a bounded wait since the
+        last poll (pn2_poll_device_error: 1 = FPS cluster exchange, 2 = tensor-core pipeline).  A bail-out
+        leaves partial outputs behind, so serving loops call this at their natural sync points."""
+        from . import _lib, tensorcore
+        flag = tensorcore.poll_device_error(self.static_in.device)
+        if flag:
+            raise _lib.Pn2Error("device-side protocol time-out (flag %d): outputs of the last replays are invalid" % flag)
 
     def __call__(self, point_clouds):
         self.static_in.copy_(point_clouds, non_blocking=True)
         if self.graph is None:
-            with torch.no_grad():
+            from . import _lib
+            with torch.no_grad(), _lib.thread_options(**self.options):
                 return self.backbone({"point_clouds": self.static_in})
         self.graph.replay()
         return self.static_out

@@ -26,7 +26,9 @@ def _sample_centres(xyz, npoint, inds):
     if npoint is None:
         return None, inds
     if inds is None:
-        inds, new_xyz = pointnet2_utils._ext.furthest_point_sampling_gather(xyz, npoint)
+        # one launch; differentiable w.r.t. xyz like the reference's gather_operation (votes carry grad:
+        # proposal_module_fcos.py:62-67 samples vote_xyz and decodes box centres from the result)
+        new_xyz, inds = pointnet2_utils.furthest_point_sample_gather(xyz.contiguous(), npoint)
         return new_xyz, inds
     xyz_flipped = xyz.transpose(1, 2).contiguous()
     new_xyz = pointnet2_utils.gather_operation(xyz_flipped, inds).transpose(1, 2).contiguous()

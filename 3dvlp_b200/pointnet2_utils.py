@@ -29,6 +29,30 @@ class FurthestPointSampling(Function):
 furthest_point_sample = FurthestPointSampling.apply
 
 
+class FurthestPointSampleGather(Function):
+    """FPS fused with the xyz gather that follows it in every SA module
+    (pointnet2_modules.py:233-240: ``gather_operation(xyz_flipped, furthest_point_sample(xyz, npoint))``)
+    in one launch: xyz (B,N,3) -> (new_xyz (B,npoint,3), inds (B,npoint) int32).  Like the
+    reference's composition, new_xyz is differentiable w.r.t. xyz (scatter-add of the incoming
+    gradient, GatherOperation.backward :108-115) and the indices are not."""
+
+    @staticmethod
+    def forward(ctx, xyz, npoint):
+        inds, new_xyz = _ext.furthest_point_sampling_gather(xyz, npoint)
+        ctx.for_backwards = (inds, xyz.size(1))
+        ctx.mark_non_differentiable(inds)
+        return new_xyz, inds
+
+    @staticmethod
+    def backward(ctx, grad_xyz, _grad_inds=None):
+        inds, n = ctx.for_backwards
+        g = _ext.gather_points_grad(grad_xyz.transpose(1, 2).contiguous(), inds, n)  # (B, 3, n)
+        return g.transpose(1, 2).contiguous(), None
+
+
+furthest_point_sample_gather = FurthestPointSampleGather.apply
+
+
 class GatherOperation(Function):
     """pointnet2_utils.py:81-115.  features (B,C,N), idx (B,npoint) -> (B,C,npoint)."""
 

@@ -105,7 +105,8 @@ class StandardROIHeads(nn.Module):
         batch_size, _, num_proposal = ROI_features.shape
         if not self.training and not torch.is_grad_enabled() and ROI_features.is_cuda:
             p = self._plan()
-            rows = getattr(ROI_features, "_pn2_rows", None)
+            from . import fused
+            rows = fused.cached_rows(ROI_features)
             if rows is None or rows.shape != (batch_size * num_proposal, 128):
                 rows = tcm.pack_rows(ROI_features.contiguous().float(), 128)
             h = tcm.linear(rows, p["l1"][0], p["l1"][1], relu=True, out="bf16")

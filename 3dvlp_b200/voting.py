@@ -67,7 +67,8 @@ class VotingModule(nn.Module):
         if (not self.training and not torch.is_grad_enabled() and seed_xyz.is_cuda and self.vote_factor == 1
                 and self.in_dim % 64 == 0 and self.in_dim <= 256):
             p = self._plan()
-            rows = getattr(seed_features, "_pn2_rows", None)
+            from . import fused
+            rows = fused.cached_rows(seed_features)
             if rows is None or rows.shape != (batch_size * num_seed, self.in_dim):
                 rows = tcm.pack_rows(seed_features.contiguous().float(), self.in_dim)
             h = tcm.linear(rows, p["l1"][0], p["l1"][1], relu=True, out="bf16")

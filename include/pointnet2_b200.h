@@ -37,6 +37,12 @@ int pn2_device_arch(int* major, int* minor); /* compute capability of the curren
 /* Synchronises `stream` and reads (then clears) the device-side protocol error flag: 0 = none,
  * 1 = FPS cluster exchange timed out, 2 = tensor-core pipeline timed out.  Debug aid. */
 int pn2_poll_device_error(int* flag_out, void* stream);
+/* Host-side launch statistics (process-wide, monotonic): how often a kernel variant was chosen --
+ * "fps_cluster_launches", "fps_bucket_launches", "fps_pair_launches", "bq_grid_launches",
+ * "bq_small_grid_launches", "bq_scan_launches", "nn_small_launches", "nn_tiled_launches".
+ * The parity tests read them to prove that the variant they mean to cover is the one that ran.
+ * Returns -1 for an unknown name. */
+long long pn2_get_stat(const char* name);
 /* Run-time options (process-wide; initial value from the environment variable in brackets):
  *   "fps_bucket" [PN2_FPS_BUCKET, default 0]  1 = large scenes (16 384..50 176 points) use the single-SM
  *                bucketed FPS kernel with spatial pruning instead of the 16-SM cluster kernel: same
@@ -49,6 +55,11 @@ int pn2_poll_device_error(int* flag_out, void* stream);
  * pn2_get_option returns the value, or -1 for an unknown name. */
 int pn2_set_option(const char* name, int value);
 int pn2_get_option(const char* name);
+/* Per-thread override of an option for calls made by the CALLING host thread only (value < 0 removes
+ * the override); pn2_get_option on that thread reports the override.  Entry points are re-entrant and
+ * may be called from several host threads (the reference is driven from DataParallel worker threads):
+ * a thread that captures a CUDA graph with other settings must not change what its neighbours launch. */
+int pn2_set_option_thread(const char* name, int value);
 
 /* ---------------------------------------------------------------------------------------------
  * The nine launchers of pointnet2._ext

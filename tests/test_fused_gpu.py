@@ -112,8 +112,14 @@ def test_sa_fused_matches_mixed_precision_contract(pkg, oracle, cuda, name):
     err = (nf.cpu() - ff).abs().max().item() / ff.abs().max().item()
     assert err < 2e-2, err
     # the bf16 point-major twin handed to the next layer
-    rows = nf._pn2_rows.float().view(b, npoint, -1).transpose(1, 2)
+    rows = nf._pn2_rows[1].float().view(b, npoint, -1).transpose(1, 2)
     torch.testing.assert_close(rows.cpu(), nf.cpu(), rtol=1e-2, atol=1e-2 * scale)
+    # an in-place edit of the fp32 tensor invalidates the twin (it is keyed on the tensor version)
+    import importlib
+    fused = importlib.import_module("3dvlp_b200.fused")
+    assert fused.cached_rows(nf) is not None
+    nf.mul_(2.0)
+    assert fused.cached_rows(nf) is None
 
 
 def test_sa_fused_user_inds_and_unnormalised(pkg, oracle, cuda):

@@ -60,6 +60,42 @@ def test_sa_module_train_mode_and_user_inds(pkg, golden, cuda):
     assert m.mlp_module.layer0.conv.weight.grad is not None
 
 
+@pytest.mark.parametrize("user_inds", [False, True])
+def test_sa_module_gradient_reaches_xyz(pkg, cuda, user_inds):
+    """d(loss)/d(xyz) through new_xyz (the FPS gather) AND through the recentred grouped coordinates, as in
+    the reference where both go through differentiable gather/group ops (pointnet2_modules.py:233-248;
+    ProposalModule samples vote_xyz, which carries grad).  Checked against torch's own indexing autograd
+    on the same indices."""
+    xyz, feats = _scene()
+    m = pkg.PointnetSAModuleVotes(npoint=40, radius=0.45, nsample=12, mlp=[5, 16, 16, 32], use_xyz=True,
+                                  normalize_xyz=True)
+    fill_state_dict(m)
+    m = m.to(cuda).eval()   # eval-mode BN keeps the comparison free of batch statistics
+    x = xyz.to(cuda).requires_grad_(True)
+    f = feats.to(cuda).requires_grad_(True)
+    inds_in = (torch.arange(40, dtype=torch.int32).repeat(2, 1) * 5).contiguous().to(cuda) if user_inds else None
+    nx, nf, ii = m(x, f, inds_in)
+    w_xyz = torch.linspace(-1, 1, nx.numel(), device=cuda).view_as(nx)
+    w_f = torch.linspace(0.5, -0.5, nf.numel(), device=cuda).view_as(nf)
+    ((nx * w_xyz).sum() + (nf * w_f).sum()).backward()
+    assert x.grad is not None and f.grad is not None
+
+    x2 = xyz.to(cuda).requires_grad_(True)
+    f2 = feats.to(cuda).requires_grad_(True)
+    idx = pkg.pointnet2_utils.ball_query(0.45, 12, xyz.to(cuda), nx.detach()).long()       # (B, 40, 12)
+    nx2 = torch.gather(x2, 1, ii.long().unsqueeze(-1).expand(-1, -1, 3))
+    b = x2.shape[0]
+    ar = torch.arange(b, device=cuda)[:, None, None]
+    local = (x2[ar, idx] - nx2.unsqueeze(2)) / 0.45                                          # (B, 40, 12, 3)
+    grouped = torch.cat([local.permute(0, 3, 1, 2), f2.transpose(1, 2)[ar, idx].permute(0, 3, 1, 2)], 1)
+    nf2 = torch.nn.functional.max_pool2d(m.mlp_module(grouped), kernel_size=[1, 12]).squeeze(-1)
+    ((nx2 * w_xyz).sum() + (nf2 * w_f).sum()).backward()
+    torch.testing.assert_close(nf, nf2, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(x.grad, x2.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(f.grad, f2.grad, rtol=1e-4, atol=1e-5)
+    assert x.grad.abs().sum() > 0
+
+
 def test_fp_module_generic_path(pkg, golden, cuda):
     unknown = cloud(31, 2, 50, extent=1.0)
     known = cloud(32, 2, 20, extent=1.0)

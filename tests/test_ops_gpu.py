@@ -46,43 +46,86 @@ FPS_CASES = {
     "bucket_identical_17000": (lambda: torch.ones(1, 17000, 3) * 0.7, 50),
     "bucket_45056_to_n": (lambda: cloud(25, 1, 45056, extent=3.0)[..., :3].contiguous(), 1500),
     "bucket_16384_m_all": (lambda: cloud(26, 1, 16384, extent=0.5)[..., :3].contiguous(), 3000),
+    # the BASELINE scene size itself, with sampling-with-replacement duplicates, a lattice and the origin skip
+    "bucket_40000_dups": (lambda: cloud(27, 1, 40000, extent=4.0, dup_frac=0.4, origin_pts=9)[..., :3].contiguous(), 2048),
+    "bucket_lattice_39304": (lambda: _lattice(34), 1200),
+    "bucket_50176_max": (lambda: cloud(28, 1, 50176, extent=5.0, dup_frac=0.1)[..., :3].contiguous(), 1024),
 }
 
 
-@pytest.mark.parametrize("name", sorted(FPS_CASES))
-def test_fps_bit_exact(pkg, oracle, cuda, name):
+def _bucket_range(n):
+    return 16384 <= n <= 50176  # fps_bucket_supported (csrc/fps_bucket.cu)
+
+
+def _fps_variants(name):
+    """Every case runs on the default kernel choice; the cases inside the bucketed kernel's range run a
+    second time with fps_bucket=1 (the variant the headline bench captures)."""
+    n = FPS_CASES[name][0]().shape[1]
+    return [0, 1] if _bucket_range(n) else [0]
+
+
+class _expect_variant:
+    """Asserts through pn2_get_stat that the FPS variant meant to be covered is the one that launched."""
+
+    def __init__(self, pkg, bucket, n):
+        self.pkg, self.bucket, self.n = pkg, bucket, n
+
+    def __enter__(self):
+        self.pkg.set_option("fps_bucket", self.bucket)
+        self.before = (self.pkg.get_stat("fps_bucket_launches"), self.pkg.get_stat("fps_cluster_launches"))
+        return self
+
+    def __exit__(self, *exc):
+        self.pkg.set_option("fps_bucket", 0)
+        if exc[0] is None:
+            db = self.pkg.get_stat("fps_bucket_launches") - self.before[0]
+            dc = self.pkg.get_stat("fps_cluster_launches") - self.before[1]
+            if self.bucket and _bucket_range(self.n):
+                assert db > 0 and dc == 0, "bucketed FPS kernel did not run (bucket %d, cluster %d launches)" % (db, dc)
+            else:
+                assert db == 0 and dc > 0, "cluster FPS kernel did not run (bucket %d, cluster %d launches)" % (db, dc)
+        return False
+
+
+@pytest.mark.parametrize("name,bucket", [(nm, v) for nm in sorted(FPS_CASES) for v in _fps_variants(nm)])
+def test_fps_bit_exact(pkg, oracle, cuda, name, bucket):
     build, m = FPS_CASES[name]
     x = build()
     want = oracle.ext.furthest_point_sampling(x, m)
-    got = pkg._ext.furthest_point_sampling(x.to(cuda), m)
-    assert got.dtype == torch.int32 and got.shape == want.shape
-    assert torch.equal(got.cpu(), want), name
-    inds2, new_xyz = pkg._ext.furthest_point_sampling_gather(x.to(cuda), m)
+    with _expect_variant(pkg, bucket, x.shape[1]):
+        got = pkg._ext.furthest_point_sampling(x.to(cuda), m)
+        assert got.dtype == torch.int32 and got.shape == want.shape
+        assert torch.equal(got.cpu(), want), name
+        inds2, new_xyz = pkg._ext.furthest_point_sampling_gather(x.to(cuda), m)
     assert torch.equal(inds2.cpu(), want)
     ref_xyz = torch.gather(x, 1, want.long().unsqueeze(-1).expand(-1, -1, 3))
     assert torch.equal(new_xyz.cpu(), ref_xyz)
 
 
-@pytest.mark.parametrize("n", [900, 9000, 20000])
-def test_fps_nan_inf_coordinates(pkg, oracle, cuda, n):
+@pytest.mark.parametrize("n,bucket", [(900, 0), (9000, 0), (20000, 0), (20000, 1), (40000, 1)])
+def test_fps_nan_inf_coordinates(pkg, oracle, cuda, n, bucket):
     x = cloud(10, 1, n)[..., :3].contiguous()
     x[0, 17, 1] = float("nan"); x[0, 400] = float("inf"); x[0, 555, 2] = float("-inf")
     want = oracle.ext.furthest_point_sampling(x, 40)
-    got = pkg._ext.furthest_point_sampling(x.to(cuda), 40)
+    with _expect_variant(pkg, bucket, n):
+        got = pkg._ext.furthest_point_sampling(x.to(cuda), 40)
     assert torch.equal(got.cpu(), want)
 
 
-def test_fps_full_scene_40k(pkg, oracle, cuda):
-    """BASELINE size: 40 000 -> 2048 on synthetic ScanNet-like scenes (duplicates + near-origin)."""
+@pytest.mark.parametrize("bucket", [0, 1])
+def test_fps_full_scene_40k(pkg, oracle, cuda, bucket):
+    """BASELINE size: 40 000 -> 2048 on synthetic ScanNet-like scenes (duplicates + near-origin), on the
+    cluster kernel and on the bucketed kernel the headline bench runs."""
     import importlib
     syn = importlib.import_module("3dvlp_b200.synthetic")
     pc = syn.make_batch(2, 2, 40000, 1)  # seeds 1002 (16k duplicates), 1003
     x = pc[..., :3].contiguous()
     want = oracle.ext.furthest_point_sampling(x, 2048)
-    got = pkg._ext.furthest_point_sampling(x.to(cuda), 2048)
-    assert torch.equal(got.cpu(), want)
-    # size-independent property: the sampled set is a prefix chain (first k of m == FPS with k)
-    got_k = pkg._ext.furthest_point_sampling(x.to(cuda), 777)
+    with _expect_variant(pkg, bucket, 40000):
+        got = pkg._ext.furthest_point_sampling(x.to(cuda), 2048)
+        assert torch.equal(got.cpu(), want)
+        # size-independent property: the sampled set is a prefix chain (first k of m == FPS with k)
+        got_k = pkg._ext.furthest_point_sampling(x.to(cuda), 777)
     assert torch.equal(got_k, got[:, :777])
 
 

@@ -82,3 +82,99 @@ def test_backbone_multiview_132_channels(pkg, cuda):
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
     assert out["sa1_features"].shape == (2, 128, 2048)
+
+
+# ---- the configurations above, against the ORACLE (not the repo's own generic path) ----------------------
+
+_IDX_KEYS = ("sa1_inds", "sa2_inds", "fp2_inds", "sa1_xyz", "sa2_xyz", "sa3_xyz", "sa4_xyz", "fp2_xyz")
+_FEAT_KEYS = ("sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features")
+
+
+def _oracle_backbone_per_scene(oracle, pc, sd, sa_cfg=None):
+    """oracle.backbone scene by scene (bounds the grouped tensors of the CPU restatement)."""
+    outs = []
+    for i in range(pc.shape[0]):
+        kw = {} if sa_cfg is None else {"sa_cfg": sa_cfg}
+        outs.append(oracle.backbone(pc[i:i + 1], sd, **kw))
+    return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+
+
+def _check_vs_oracle(got, want, feat_tol=3e-2):
+    for k in _IDX_KEYS:
+        assert torch.equal(got[k].cpu(), want[k]), k     # bit-exact indices and sampled coordinates
+    errs = {}
+    for k in _FEAT_KEYS:
+        a, b = got[k].float().cpu(), want[k]
+        assert torch.isfinite(a).all(), k
+        # bf16 tensor-core operands, fp32 accumulation, against the fp32 reference semantics: stated
+        # tolerance 3e-2 of the tensor's max (the contract of DESIGN.md section 4, "Numerics")
+        errs[k] = (a - b).abs().max().item() / b.abs().max().item()
+        assert errs[k] < feat_tol, (k, errs[k])
+    return errs
+
+
+def test_bench_config_vs_oracle(pkg, oracle, cuda):
+    """The exact configuration bench.py times -- GraphedBackbone(throughput=True): bucketed single-SM FPS,
+    sa_tiles_per_group = 16, CUDA-graph replay -- on 8 scenes x 40 000 points x (xyz + height), seeds
+    1000..1007 (1002 carries 16k sampling-with-replacement duplicates), against oracle.backbone."""
+    from common import fill_state_dict
+    bb = pkg.Pointnet2Backbone(input_feature_dim=1)
+    sd = fill_state_dict(bb)
+    bb = bb.to(cuda).eval()
+    pc = _scene(0, 8, 40000, 1)
+    before = pkg.get_stat("fps_bucket_launches")
+    g = pkg.GraphedBackbone(bb, pc.to(cuda), throughput=True)
+    assert g.graph is not None, g.capture_error
+    assert g.options == {"fps_bucket": 1, "sa_tiles_per_group": 16}
+    assert pkg.get_stat("fps_bucket_launches") > before, "the bucketed FPS kernel was not captured"
+    assert pkg.get_option("fps_bucket") == 0 and pkg.get_option("sa_tiles_per_group") == 0  # per-thread, restored
+    out = g(pc.to(cuda))
+    torch.cuda.synchronize()
+    g.check()
+    got = {k: out[k].clone() for k in _IDX_KEYS + _FEAT_KEYS}
+    want = _oracle_backbone_per_scene(oracle, pc, sd)
+    errs = _check_vs_oracle(got, want)
+    print("bench-config feature errors (max-norm, vs fp32 oracle):", {k: round(v, 5) for k, v in errs.items()})
+    # a second replay on another batch (duplicate-heavy seeds) reuses the captured kernels
+    pc2 = _scene(40, 8, 40000, 1)
+    out = g(pc2.to(cuda))
+    torch.cuda.synchronize()
+    want2 = _oracle_backbone_per_scene(oracle, pc2, sd)
+    _check_vs_oracle({k: out[k] for k in _IDX_KEYS + _FEAT_KEYS}, want2)
+
+
+def test_backbone_multiview_132_channels_vs_oracle(pkg, oracle, cuda):
+    """BASELINE config 4 (40k points x 135 input columns): the gather-mode SA1 kernel (per-point tensor-core
+    GEMM g, then grouped layer 1) against the oracle -- fp32 semantics at the stated tolerance and the
+    mixed-precision restatement at rtol 1e-3."""
+    from common import fill_state_dict
+    bb = pkg.Pointnet2Backbone(input_feature_dim=132)
+    sd = fill_state_dict(bb)
+    bb = bb.to(cuda).eval()
+    pc = _scene(31, 2, 40000, 132)
+    with torch.no_grad():
+        got = bb({"point_clouds": pc.to(cuda)})
+    assert bb.sa1._fused not in (None, False) and not bb.sa1._fused.direct
+    want = _oracle_backbone_per_scene(oracle, pc, sd)
+    _check_vs_oracle(got, want)
+    xyz = pc[..., :3].contiguous()
+    feats = pc[..., 3:].transpose(1, 2).contiguous()
+    for i in range(2):
+        _, wf, _ = oracle.sa_module_mixed(xyz[i:i + 1], feats[i:i + 1], sd, "sa1.", 2048, 0.2, 64, normalize_xyz=True)
+        scale = wf.abs().max().item()
+        torch.testing.assert_close(got["sa1_features"][i:i + 1].cpu(), wf, rtol=1e-3, atol=4e-3 * scale)
+
+
+def test_backbone_100k_points_npoint_4096_vs_oracle(pkg, oracle, cuda):
+    """BASELINE config 5's largest shape (100k-point scene, SA1 npoint 4096) against oracle.backbone."""
+    from common import fill_state_dict
+    bb = pkg.Pointnet2Backbone(input_feature_dim=1)
+    sd = fill_state_dict(bb)
+    bb = bb.to(cuda).eval()
+    bb.sa1.npoint = 4096
+    pc = _scene(21, 1, 100000, 1)
+    with torch.no_grad():
+        got = bb({"point_clouds": pc.to(cuda)})
+    cfg = (("sa1", 4096, 0.2, 64),) + tuple(oracle.BACKBONE_SA[1:])
+    want = oracle.backbone(pc, sd, sa_cfg=cfg)
+    _check_vs_oracle(got, want)
