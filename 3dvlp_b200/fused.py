@@ -208,12 +208,15 @@ def backbone_forward(bb, data_dict):
         rows1 = tcm.pack_point_rows(pc, 3, plans[0].c_in, plans[0].w1f.kpad)
     dev = xyz.device
     main = torch.cuda.current_stream(dev)
-    side = _side_streams.get(dev)
+    # the helper streams take the caller's stream priority: kernels captured into a CUDA graph keep the
+    # priority of the stream they were captured on, and a serving loop uses it to stagger its batches
+    prio = main.priority
+    side = _side_streams.get((dev, prio))
     if side is None:
-        side = _side_streams[dev] = torch.cuda.Stream(device=dev)
-    aux = _aux_streams.get(dev)
+        side = _side_streams[(dev, prio)] = torch.cuda.Stream(device=dev, priority=prio)
+    aux = _aux_streams.get((dev, prio))
     if aux is None:
-        aux = _aux_streams[dev] = torch.cuda.Stream(device=dev)
+        aux = _aux_streams[(dev, prio)] = torch.cuda.Stream(device=dev, priority=prio)
     capturing = torch.cuda.is_current_stream_capturing()
     side.wait_stream(main)
     aux.wait_stream(main)

@@ -18,7 +18,7 @@ class GraphedBackbone:
     next call.  Falls back to eager execution (``self.graph is None``) if capture is not possible.
     """
 
-    def __init__(self, backbone, example_batch, warmup=3, throughput=False):
+    def __init__(self, backbone, example_batch, warmup=3, throughput=False, priority=0):
         if backbone.training:
             raise RuntimeError("GraphedBackbone needs the backbone in eval() mode")
         if not example_batch.is_cuda or example_batch.dtype != torch.float32:
@@ -40,7 +40,12 @@ class GraphedBackbone:
             self.static_out = None
             self.capture_error = None
             cur = torch.cuda.current_stream(self.static_in.device)
-            s = torch.cuda.Stream(device=self.static_in.device)
+            # `priority` (0 = default, negative = higher): every kernel of the graph is captured on streams
+            # of that priority and keeps it on replay.  A serving loop with several graphs in flight gives
+            # them descending priorities so that batches complete one after the other -- their device->host
+            # reads overlap the compute of the batches behind them -- instead of all at once.
+            s = torch.cuda.Stream(device=self.static_in.device, priority=priority)
+            self.priority = s.priority
             s.wait_stream(cur)
             with torch.no_grad(), torch.cuda.stream(s):
                 for _ in range(max(1, warmup)):  # fills every host-side cache (plans, occupancy, pools)
@@ -49,7 +54,7 @@ class GraphedBackbone:
             torch.cuda.synchronize(self.static_in.device)
             try:
                 g = torch.cuda.CUDAGraph()
-                with torch.no_grad(), torch.cuda.graph(g):
+                with torch.no_grad(), torch.cuda.graph(g, stream=s):
                     out = backbone({"point_clouds": self.static_in})
                 self.graph, self.static_out = g, out
             except Exception as ex:  # pragma: no cover - depends on driver behaviour

@@ -1,15 +1,23 @@
-"""Vote and objectness losses -- the two live call sites of nn_distance.
+"""Detection losses -- the callers that define nn_distance's live shapes and consume its assignment.
 
-Mirror of /root/reference/lib/loss_helper/loss_detection.py:24-113 (``compute_vote_loss``,
-``compute_objectness_loss``).  Same data_dict keys, constants and
-return values; the pairwise matching runs on the fused nn_distance kernel (one launch per direction,
-differentiable) instead of the reference's repeat/sub/abs/sum/min chain, and nothing is pinned to
-``.cuda()`` (the reference hard-codes it): tensors follow the inputs' device.
+Mirror of /root/reference/lib/loss_helper/loss_detection.py:
+``compute_vote_loss`` (:24-71), ``compute_objectness_loss`` (:73-113), ``compute_box_loss`` (:116-153),
+``recover_assigned_gt_bboxes`` (:156-211) and ``compute_box_and_sem_cls_loss`` (:215-258).  Same
+data_dict keys, constants, return values and side effects (``gt_assigned_*`` entries).  The pairwise
+matching runs on the fused nn_distance kernel (one launch per direction, differentiable) instead of the
+reference's repeat/sub/abs/sum/min chain; the box assignment gathers through ``object_assignment`` without
+the reference's ``.repeat`` / ``torch.ones(B,N,num_size_cluster,3)`` materialisations; nothing is pinned
+to ``.cuda()`` (the reference hard-codes it, SURVEY appendix C-7: tensors follow the inputs' device) and
+nothing synchronises with the host.  Pinned against the reference's own functions by
+tests/golden/reference_losses.npz (tests/golden/make_golden_losses.py).
 """
+import math
+
 import torch
 import torch.nn.functional as F
 
-from .nn_distance import nn_distance
+from .box_util import rotz_batch_pytorch
+from .nn_distance import huber_loss, nn_distance
 
 FAR_THRESHOLD = 0.3
 NEAR_THRESHOLD = 0.3
@@ -57,3 +65,127 @@ def compute_objectness_loss(data_dict):
     loss = F.cross_entropy(objectness_scores.transpose(2, 1), objectness_label, weight=weight, reduction='none')
     objectness_loss = torch.sum(loss * objectness_mask) / (torch.sum(objectness_mask) + 1e-6)
     return objectness_loss, objectness_label, objectness_mask, ind1
+
+
+def compute_box_loss(data_dict, config, distance_huber_loss_thres=0.15, use_centerness=False):
+    """Heading class / heading residual / six-face distance losses over the positive proposals
+    (loss_detection.py:116-153).  Returns (heading_class_loss, heading_residual_normalized_loss,
+    distance_loss)."""
+    assert not use_centerness
+    num_heading_bin = config.num_heading_bin
+    gt_heading_class = data_dict['gt_assigned_heading_class']        # (B, N)
+    gt_heading_residual = data_dict['gt_assigned_heading_residual']  # (B, N)
+    gt_distance = data_dict['gt_assigned_distance']                  # (B, N, 6)
+    objectness_label = data_dict['objectness_label'].float()         # (B, N)
+    n_pos = torch.sum(objectness_label) + 1e-6
+
+    heading_class_loss = F.cross_entropy(data_dict['heading_scores'].transpose(2, 1), gt_heading_class, reduction='none')
+    heading_class_loss = torch.sum(heading_class_loss * objectness_label) / n_pos
+
+    heading_residual_normalized_label = gt_heading_residual / (math.pi / num_heading_bin)
+    # the reference multiplies by a scattered one-hot and sums over the bins: a gather of the labelled bin
+    picked = torch.gather(data_dict['heading_residuals_normalized'], 2, gt_heading_class.unsqueeze(-1)).squeeze(-1)
+    heading_residual_normalized_loss = huber_loss(picked - heading_residual_normalized_label, delta=1.0)
+    heading_residual_normalized_loss = torch.sum(heading_residual_normalized_loss * objectness_label) / n_pos
+
+    distance_loss = torch.mean(huber_loss(data_dict['rois'] - gt_distance, delta=distance_huber_loss_thres), -1)
+    distance_loss = torch.sum(distance_loss * objectness_label) / n_pos
+    return heading_class_loss, heading_residual_normalized_loss, distance_loss
+
+
+def _mean_sizes(config, like):
+    mean = getattr(config, "mean_size_arr_tensor", None)
+    if mean is None or mean.device != like.device:
+        mean = torch.as_tensor(config.mean_size_arr, dtype=torch.float32).to(like.device)
+    return mean.to(like.dtype)
+
+
+def recover_assigned_gt_bboxes(data_dict, config, object_assignment):
+    """The ground-truth box assigned to every proposal and the proposal's distances to its six faces
+    (loss_detection.py:156-211).  Returns (gt_center (B,N,3), heading_class_label (B,N),
+    heading_residual_label (B,N), gt_heading (B,N), gt_distance (B,N,6), inside_label (B,N) long,
+    gt_centerness (B,N), gt_bbox_size (B,N,3))."""
+    num_heading_bin = config.num_heading_bin
+    xyz = data_dict['aggregated_vote_xyz']                                       # (B, N, 3)
+    idx3 = object_assignment.unsqueeze(-1).expand(-1, -1, 3)
+    gt_center = torch.gather(data_dict['center_label'], 1, idx3)
+    heading_class_label = torch.gather(data_dict['heading_class_label'], 1, object_assignment)
+    heading_residual_label = torch.gather(data_dict['heading_residual_label'], 1, object_assignment)
+    if num_heading_bin != 1:  # SUN RGB-D
+        gt_heading = heading_class_label.float() * ((2 * math.pi) / float(num_heading_bin)) + heading_residual_label
+    else:                     # ScanNet: axis-aligned boxes
+        gt_heading = torch.zeros(object_assignment.shape, device=xyz.device)
+
+    size_class_label = torch.gather(data_dict['size_class_label'], 1, object_assignment)
+    size_residual_label = torch.gather(data_dict['size_residual_label'], 1, idx3)
+    gt_bbox_size = _mean_sizes(config, size_residual_label)[size_class_label] + size_residual_label
+    half = gt_bbox_size / 2
+
+    # the proposal in the frame of its box: recentre, rotate by -heading (row vector times R)
+    local = xyz - gt_center
+    R = rotz_batch_pytorch(-gt_heading.float())                                  # (B, N, 3, 3)
+    local = torch.matmul(local.unsqueeze(-2), R).squeeze(-2)
+    bld = half + local   # back / left / down face distances
+    fru = half - local   # front / right / up
+    gt_distance = torch.cat((bld, fru), dim=2)
+    inside_label = torch.eq(torch.sum(torch.gt(gt_distance, 0), dim=2), 6).long()
+
+    ratio = torch.clamp(torch.min(bld, fru) / (torch.max(bld, fru) + 1e-6), min=1e-6)
+    gt_centerness = torch.pow(ratio[:, :, 0] * ratio[:, :, 1] * ratio[:, :, 2], exponent=1 / 3)
+    gt_centerness = gt_centerness * inside_label.float()
+    return (gt_center, heading_class_label, heading_residual_label, gt_heading, gt_distance, inside_label,
+            gt_centerness, gt_bbox_size)
+
+
+def compute_box_and_sem_cls_loss(data_dict, config):
+    """Box and semantic-class losses of the proposals against their assigned ground truth
+    (loss_detection.py:215-258).  Reads ``object_assignment`` / ``objectness_label`` (written by the
+    caller from compute_objectness_loss, lib/loss_helper/loss_joint.py:44-50), writes the
+    ``gt_assigned_*`` entries, returns (heading_class_loss, heading_residual_normalized_loss,
+    distance_loss, sem_cls_loss)."""
+    object_assignment = data_dict['object_assignment']
+    (gt_center, gt_heading_class, gt_heading_residual, gt_heading, gt_distance, _inside, gt_centerness,
+     _size) = recover_assigned_gt_bboxes(data_dict, config, object_assignment)
+    data_dict['gt_assigned_center'] = gt_center
+    data_dict['gt_assigned_heading_class'] = gt_heading_class
+    data_dict['gt_assigned_heading_residual'] = gt_heading_residual
+    data_dict['gt_assigned_heading'] = gt_heading
+    data_dict['gt_assigned_distance'] = gt_distance
+    data_dict['gt_assigned_centerness'] = gt_centerness
+
+    heading_class_loss, heading_residual_normalized_loss, distance_loss = compute_box_loss(
+        data_dict, config, distance_huber_loss_thres=0.15)
+
+    objectness_label = data_dict["objectness_label"]
+    sem_cls_label = torch.gather(data_dict['sem_cls_label'], 1, object_assignment)   # (B,K) from (B,K2)
+    sem_cls_loss = F.cross_entropy(data_dict['sem_cls_scores'].transpose(2, 1), sem_cls_label, reduction='none')
+    sem_cls_loss = torch.sum(sem_cls_loss * objectness_label.float()) / (torch.sum(objectness_label) + 1e-6)
+    return heading_class_loss, heading_residual_normalized_loss, distance_loss, sem_cls_loss
+
+
+def get_detection_loss(data_dict, config):
+    """The detection part of lib/loss_helper/loss_joint.py:39-75 (``get_joint_loss`` with detection=True):
+    vote, objectness, box and semantic-class losses, the bookkeeping entries, and
+    ``box_loss = 0.1 heading_cls + heading_reg + 0.1 sem_cls + 20 size_distance``.  Returns data_dict."""
+    vote_loss = compute_vote_loss(data_dict)
+    objectness_loss, objectness_label, objectness_mask, object_assignment = compute_objectness_loss(data_dict)
+    total = objectness_label.shape[0] * objectness_label.shape[1]
+    data_dict["objectness_label"] = objectness_label
+    data_dict["objectness_mask"] = objectness_mask
+    data_dict["object_assignment"] = object_assignment
+    data_dict["pos_ratio"] = torch.sum(objectness_label.float()) / float(total)
+    data_dict["neg_ratio"] = torch.sum(objectness_mask.float()) / float(total) - data_dict["pos_ratio"]
+    heading_cls_loss, heading_reg_loss, size_distance_loss, sem_cls_loss = compute_box_and_sem_cls_loss(data_dict, config)
+    box_loss = 0.1 * heading_cls_loss + heading_reg_loss + 0.1 * sem_cls_loss
+    box_loss = box_loss + 20 * size_distance_loss
+    obj_pred_val = torch.argmax(data_dict["objectness_scores"], 2)
+    data_dict["obj_acc"] = torch.sum((obj_pred_val == objectness_label.long()).float() * objectness_mask) / (
+        torch.sum(objectness_mask) + 1e-6)
+    data_dict["vote_loss"] = vote_loss
+    data_dict["objectness_loss"] = objectness_loss
+    data_dict["heading_cls_loss"] = heading_cls_loss
+    data_dict["heading_reg_loss"] = heading_reg_loss
+    data_dict["size_distance_loss"] = size_distance_loss
+    data_dict["sem_cls_loss"] = sem_cls_loss
+    data_dict["box_loss"] = box_loss
+    return data_dict

@@ -6,7 +6,10 @@ for j in range(len_nun_max):`` in Python, calling box3d_diou_batch_tensor (~45 t
 (scene, sentence) and reading ``max_ious`` / ``cnt`` back to the host for its ``if``s.  Here the IoU /
 DIoU of all (scene, sentence, proposal) triples is one kernel (box_util.box3d_diou_pairs) and the label
 logic is a handful of masked tensor ops: same labels, same losses, no host synchronisation
-(``max_iou_rate_*`` stay 0-dim device tensors instead of numpy scalars).
+(``max_iou_rate_*`` stay 0-dim device tensors instead of numpy scalars).  Pinned against the reference's
+own function, imported with stand-ins for the packages this image lacks, by
+tests/golden/reference_losses.npz (tests/golden/make_golden_losses.py): eight configurations, values
+and gradients.
 """
 import torch
 import torch.nn as nn
@@ -40,16 +43,19 @@ def gt_boxes_from_labels(data_dict, config):
 def compute_diou_loss(data_dict, config, no_reference=False, use_reg_head=False, use_kl_loss=False, debug=False):
     """loss_grounding.py:129-365.  Returns (data_dict, ref_loss, cluster_preds (B,L,K), cluster_labels
     (B,L,K) float one-hot of the best-IoU proposal where it reaches 0.25); writes ``diou_loss``,
-    ``max_iou_rate_0.25`` / ``_0.5`` (and ``kl_loss``) into data_dict like the reference."""
-    if debug:
-        raise NotImplementedError("compute_diou_loss: the reference's debug statistics are not part of the hot path")
+    ``max_iou_rate_0.25`` / ``_0.5`` (``kl_loss`` with use_kl_loss) and the statistics keys the reference
+    solver reads unconditionally (lib/joint/solver_3dvlp.py:651-661,687-697: ``top_ind``,
+    ``pred_iou_rate_*``, ``class_iou_rate_*``, ``class_size_*``, ``top_iou_rate_*`` -- zeros unless
+    ``debug``) into data_dict like the reference.  Statistics are 0-dim device tensors where the reference
+    stores numpy scalars: nothing here synchronises with the host."""
     pred_center = data_dict['pred_center']
     pred_size = data_dict['pred_size']
+    dev = pred_center.device
     gt_center, gt_size = gt_boxes_from_labels(data_dict, config)          # (B,L,3)
     B, K = data_dict['aggregated_vote_features'].shape[:2]
     Lmax = gt_center.shape[1]
-    lang_num = data_dict["lang_num"].to(pred_center.device)
-    valid = torch.arange(Lmax, device=pred_center.device)[None, :] < lang_num[:, None]  # (B,L)
+    lang_num = data_dict["lang_num"].to(dev)
+    valid = torch.arange(Lmax, device=dev)[None, :] < lang_num[:, None]   # (B,L)
     cluster_preds = data_dict["cluster_ref"].reshape(B, Lmax, K)
     objectness_masks = data_dict['objectness_scores'].max(2)[1].float()    # (B,K)
 
@@ -64,9 +70,14 @@ def compute_diou_loss(data_dict, config, no_reference=False, use_reg_head=False,
         ious, dious = box3d_diou_pairs(pred_center, pred_size, gt_center, gt_size)
 
     ious_np = ious.detach()
-    if int(data_dict["istrain"][0]) == 1 and not no_reference and data_dict["random"] < 0.5:
-        ious = ious * objectness_masks[:, None, :]
-    ious = ious.detach()  # only used for labels below (the reference's smooth_labels are detached too)
+    ious = ious_np  # only used for labels below (the reference's smooth_labels are detached too)
+    if not no_reference and data_dict["random"] < 0.5:
+        # loss_grounding.py:237-238: in training, half of the steps only rank proposals predicted as objects.
+        # `istrain` may be a device tensor: folded into a select instead of read back
+        istrain = data_dict["istrain"]
+        istrain = istrain[0] if torch.is_tensor(istrain) or isinstance(istrain, (list, tuple)) else istrain
+        train = torch.as_tensor(istrain, device=dev) == 1
+        ious = torch.where(train, ious * objectness_masks[:, None, :], ious)
 
     ind_np = ious_np.argmax(-1)                                            # (B,L)
     max_ious = ious_np.gather(-1, ind_np.unsqueeze(-1)).squeeze(-1)
@@ -93,20 +104,60 @@ def compute_diou_loss(data_dict, config, no_reference=False, use_reg_head=False,
     diou_loss = ((1 - dious) * smooth * valid[..., None]).sum() / B
     data_dict['diou_loss'] = diou_loss
 
-    if use_kl_loss:  # loss_grounding.py:303-316 (including its size term, which compares pred with pred)
+    if use_kl_loss:  # loss_grounding.py:303-316 (including its size term, which compares pred with pred: zero)
         alpha = data_dict["alpha"]
         alpha_center, alpha_size = alpha[:, :, 0:3], alpha[:, :, 4:6]
-        crit = nn.SmoothL1Loss()
-        kl = pred_center.new_zeros(())
-        for i in range(B):
-            n_i = int(lang_num[i])
-            kl_pred_center = pred_center[i][ind_np[i, :n_i]].detach()
-            kl_pred_size = pred_size[i][ind_np[i, :n_i]].detach()
-            kl = kl + torch.sum(torch.exp(-alpha_center[i]) * crit(kl_pred_center, gt_center[i, :n_i]) + 0.5 * alpha_center[i])
-            kl = kl + torch.sum(torch.exp(-alpha_size[i]) * crit(kl_pred_size, kl_pred_size) + 0.5 * alpha_size[i])
+        picked = torch.gather(pred_center.detach(), 1, ind_np.unsqueeze(-1).expand(-1, -1, 3))       # (B,L,3)
+        sl1 = F.smooth_l1_loss(picked, gt_center, reduction='none') * valid[..., None]
+        per_scene = sl1.sum((1, 2)) / (3 * lang_num.clamp(min=1)).to(sl1.dtype)                      # nn.SmoothL1Loss() mean
+        kl = torch.sum(torch.exp(-alpha_center) * per_scene[:, None, None] + 0.5 * alpha_center) + torch.sum(0.5 * alpha_size)
         data_dict['kl_loss'] = kl / B
 
     total = lang_num.sum().to(torch.float32)
     data_dict['max_iou_rate_0.25'] = hit25.sum() / total
     data_dict['max_iou_rate_0.5'] = hit5.sum() / total
+    if debug:
+        _debug_statistics(data_dict, ious_np, cluster_preds, gt_size, valid, total)
+    else:
+        data_dict['top_ind'] = 0
+        data_dict['pred_iou_rate_0.25'] = 0
+        data_dict['pred_iou_rate_0.5'] = 0
+        for i in range(0, 18):
+            data_dict[f'class_iou_rate_{i}'] = 0
+            data_dict[f'class_size_{i}'] = 0
+        for i in range(1, 6):
+            data_dict[f'top_iou_rate_{i}'] = 0
     return data_dict, loss, cluster_preds, labels.detach()
+
+
+def _debug_statistics(data_dict, ious, cluster_preds, gt_size, valid, total):
+    """The reference's ``debug=True`` bookkeeping (loss_grounding.py:170-180,263-278,293-299,325-340) for
+    all (scene, sentence) pairs at once: rank of the predicted proposal in the IoU order, IoU hit rates,
+    per-class IoU / box volume, the five best IoUs.  Ties in the IoU order (many proposals at 0) are
+    resolved by index (a stable argsort -- what torch.sort on the CPU does; the reference does not say)."""
+    B, Lmax, K = ious.shape
+    vf = valid.to(ious.dtype)
+    n_valid = vf.sum().clamp(min=1)
+    sort_ious, sort_ind = torch.sort(ious, dim=-1, stable=True)                       # ascending
+    pred = cluster_preds.argmax(-1)                                                   # (B,L)
+    rank = (sort_ind == pred.unsqueeze(-1)).float().argmax(-1).to(ious.dtype)         # position of the prediction
+    per_scene = (rank * vf).sum(1) / vf.sum(1).clamp(min=1)
+    data_dict['top_ind'] = per_scene.mean() + 1
+    data_dict['pred_iou_rate_0.25'] = (((ious >= 0.25).to(ious.dtype).mean(-1)) * vf).sum() / n_valid
+    data_dict['pred_iou_rate_0.5'] = (((ious >= 0.5).to(ious.dtype).mean(-1)) * vf).sum() / n_valid
+    top5 = (sort_ious[..., -5:] * vf[..., None]).sum((0, 1))                          # ascending: [-1] is the best
+    for i in range(1, 6):
+        data_dict[f'top_iou_rate_{i}'] = top5[5 - i] / total
+    cat = data_dict["object_cat_list"].long().to(ious.device)[:, :Lmax].reshape(-1)
+    flat_valid = vf.reshape(-1)
+    iou_at_pred = ious.gather(-1, pred.unsqueeze(-1)).squeeze(-1).reshape(-1) * flat_valid
+    volume = gt_size.prod(-1).reshape(-1) * flat_valid
+    zeros = torch.zeros(18, device=ious.device, dtype=ious.dtype)
+    class_iou = zeros.index_add(0, cat, iou_at_pred)
+    class_size = zeros.index_add(0, cat, volume)
+    class_cnt = zeros.index_add(0, cat, flat_valid)
+    class_cnt = torch.where(class_cnt == 0, torch.ones_like(class_cnt), class_cnt)
+    class_iou, class_size = class_iou / class_cnt, class_size / class_cnt
+    for i in range(0, 18):
+        data_dict[f'class_iou_rate_{i}'] = class_iou[i]
+        data_dict[f'class_size_{i}'] = class_size[i]

@@ -181,57 +181,74 @@ def cpu_reference_arm(args, torch, pkg, syn):
     print(json.dumps(line), flush=True)
 
 
-def reference_cuda_ext_leg(torch, pkg, model, dev_pool, steps):
-    """Time the UNMODIFIED reference CUDA extension (oracle/_ref/pointnet2_ref_ext.so, built by
-    oracle/build_ref.py) driving the same module tree op by op exactly like the reference's Python
-    layers (FPS -> gather -> ball_query -> group x2 -> cuDNN SharedMLP -> max_pool; three_nn ->
-    three_interpolate -> cuDNN MLP).  This is the "reference CUDA-extension semantics" bar of the
-    north star; it is a measured baseline, never part of the product path."""
+def _load_reference_stack():
+    """The reference's OWN Python stack from baseline/_ref (laid out by oracle/build_ref.py, git-ignored):
+    its pointnet2_utils / pointnet2_modules / pytorch_utils / backbone_module, bound to its OWN compiled
+    extension (oracle/_ref/pointnet2_ref_ext.so registered under the name its Python layer imports,
+    ``pointnet2._ext``, lib/pointnet2/pointnet2_utils.py:25-33).  Returns the stock Pointnet2Backbone
+    class, or None when either half is missing."""
     import importlib.util
+    import types
     so = os.path.join(ROOT, "oracle", "_ref", "pointnet2_ref_ext.so")
-    if not os.path.exists(so):
+    base = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(so) or not os.path.exists(os.path.join(base, "models", "base_module", "backbone_module.py")):
         return None
     spec = importlib.util.spec_from_file_location("pointnet2_ref_ext", so)
     ref = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ref)
-
-    class Shim:
-        def __getattr__(self, name):
-            return getattr(ref, name)
-
-        @staticmethod
-        def furthest_point_sampling_gather(xyz, npoint):  # pointnet2_modules.py:233-240
-            inds = ref.furthest_point_sampling(xyz, npoint)
-            flipped = xyz.transpose(1, 2).contiguous()
-            return inds, ref.gather_points(flipped, inds).transpose(1, 2).contiguous()
-
-    utils = pkg.pointnet2_utils
-    saved_ext = utils._ext
-    saved = {}
-    for name, m in model.named_modules():
-        if hasattr(m, "_fused"):
-            saved[name] = m._fused
-            m._fused = False  # generic op-by-op path
-    utils._ext = Shim()
+    parent = types.ModuleType("pointnet2")
+    parent.__path__ = []
+    parent._ext = ref
+    sys.modules["pointnet2"] = parent
+    sys.modules["pointnet2._ext"] = ref
+    saved_path = list(sys.path)
+    shadowed = {k: sys.modules.pop(k) for k in list(sys.modules)
+                if k in ("lib", "models", "utils", "pointnet2_utils", "pointnet2_modules", "pytorch_utils")
+                or k.startswith(("lib.", "models.", "utils."))}
     try:
-        with torch.no_grad():
-            for s in range(2):
-                model({"point_clouds": dev_pool[s % POOL]})
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for s in range(steps):
-                model({"point_clouds": dev_pool[(2 + s) % POOL]})
-            e1.record()
-            torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        sys.path.insert(0, base)
+        sys.path.insert(0, os.path.join(base, "lib", "pointnet2"))
+        mod = importlib.import_module("models.base_module.backbone_module")
+        assert os.path.realpath(mod.__file__).startswith(os.path.realpath(base)), mod.__file__
+        return mod.Pointnet2Backbone
     finally:
-        utils._ext = saved_ext
-        for name, m in model.named_modules():
-            if name in saved:
-                m._fused = saved[name]
+        sys.path[:] = saved_path
+        for k, v in shadowed.items():
+            sys.modules.setdefault(k, v)
+
+
+def reference_cuda_ext_leg(torch, pkg, model, dev_pool, steps):
+    """GPU baseline = the UNMODIFIED reference, stock code path: its own ``Pointnet2Backbone``
+    (models/base_module/backbone_module.py:76-135) over its own pointnet2_modules / pointnet2_utils and
+    its own compiled CUDA extension, with this run's weights loaded through ``load_state_dict`` (same 96
+    keys) and the same input batches.  None of this repo's modules, kernels or host layer is on that path.
+    This is the "reference CUDA-extension semantics" bar of the north star; a measured baseline only."""
+    RefBackbone = _load_reference_stack()
+    if RefBackbone is None:
+        return None
+    dev = dev_pool[0].device
+    ref_model = RefBackbone(input_feature_dim=C_IN)
+    ref_model.load_state_dict(model.state_dict(), strict=True)
+    ref_model = ref_model.to(dev).eval()
+    with torch.no_grad():
+        for s in range(2):
+            out = ref_model({"point_clouds": dev_pool[s % POOL]})
+        torch.cuda.synchronize()
+        # the stock stack and the product must agree on what they compute: indices exactly
+        mine = model({"point_clouds": dev_pool[1 % POOL]})
+        same_inds = bool(torch.equal(out["fp2_inds"].int(), mine["fp2_inds"].int()) and torch.equal(out["sa2_inds"], mine["sa2_inds"]))
+        feat_err = float((out["fp2_features"] - mine["fp2_features"].float()).abs().max() / out["fp2_features"].abs().max())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            ref_model({"point_clouds": dev_pool[(2 + s) % POOL]})
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
     return {"value": SCENES_PER_GPU / (ms * 1e-3), "unit": "scenes/s", "ms_per_step": ms, "steps": steps,
-            "what": "unmodified reference _ext (sm_100a build) + torch/cuDNN layers, same inputs, 1 GPU"}
+            "indices_equal_to_product": same_inds, "fp2_features_max_norm_diff": feat_err,
+            "what": "UNMODIFIED reference: its Pointnet2Backbone + pointnet2_modules/utils (baseline/_ref) on its own "
+                    "_ext (sm_100a build) + torch/cuDNN layers, same weights and inputs, 1 GPU"}
 
 
 def algorithmic_work():
@@ -283,6 +300,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=20, help="batches in flight (graph replays on separate streams)")
+    ap.add_argument("--lane-priorities", type=int, default=1,
+                    help="1: the lanes (and the kernels of their graphs) get descending stream priorities, so batches in "
+                         "flight complete one after the other and their device->host reads overlap later compute")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -332,8 +352,18 @@ def main():
     # graph replays on two streams overlap one batch's sampling chain with the other's feature path.
     depth = max(1, args.depth)
     throughput_mode = depth >= 6  # many batches in flight: 1-SM bucketed FPS; few: 16-SM cluster FPS
-    graphs = [pkg.GraphedBackbone(model, dev_pool[0], throughput=throughput_mode) for _ in range(depth)]
-    lanes = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+    try:
+        least, greatest = torch.cuda.Stream.priority_range()
+    except Exception:
+        least, greatest = 0, -1
+    levels = least - greatest + 1 if args.lane_priorities else 1
+
+    def lane_priority(k):
+        return greatest + (k * levels) // depth if levels > 1 else 0
+
+    graphs = [pkg.GraphedBackbone(model, dev_pool[0], throughput=throughput_mode, priority=lane_priority(k))
+              for k in range(depth)]
+    lanes = [torch.cuda.Stream(device=dev, priority=lane_priority(k)) for k in range(depth)]
     graphed = graphs[0]
     execution = "cuda_graph" if graphed.graph is not None else "eager (graph capture failed: %s)" % graphed.capture_error
     main_stream = torch.cuda.current_stream(dev)
@@ -471,7 +501,7 @@ def main():
                     "c_in": C_IN, "l2": "rotating pool of %d input batches (%.0f MB > L2)" % (
                         POOL, POOL * SCENES_PER_GPU * N_POINTS * 4 * (3 + C_IN) / 1e6),
                     "parallelism": "scene-sharded dp%d, no data-path collective" % world,
-                    "execution": execution, "batches_in_flight": depth,
+                    "execution": execution, "batches_in_flight": depth, "lane_priority_levels": levels,
                     "fps_algorithm": "bucketed single-SM (throughput mode)" if throughput_mode else "16-CTA cluster (latency mode)"},
                 "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
@@ -502,7 +532,7 @@ def main():
                                              "what": "backbone + VotingModule + L2 norm + vote aggregation (256 clusters), "
                                                      "eager, one batch in flight"}
                 # the same front end the way the backbone is measured: CUDA-graph replays, `depth` batches in flight
-                fgraphs = [pkg.GraphedBackbone(fe, dev_pool[0], throughput=throughput_mode) for _ in range(depth)]
+                fgraphs = [pkg.GraphedBackbone(fe, dev_pool[0], throughput=throughput_mode, priority=lane_priority(k)) for k in range(depth)]
                 if all(g.graph is not None for g in fgraphs):
                     def fe_steps(count):
                         for st in lanes:
@@ -532,7 +562,7 @@ def main():
                 det.proposal.vote_aggregation = fe.proposal.vote_aggregation
                 syn.randomize_bn_stats(det.proposal.proposal)
                 det = det.eval().to(dev)
-                dgraphs = [pkg.GraphedBackbone(det, dev_pool[0], throughput=throughput_mode) for _ in range(depth)]
+                dgraphs = [pkg.GraphedBackbone(det, dev_pool[0], throughput=throughput_mode, priority=lane_priority(k)) for k in range(depth)]
                 if all(g.graph is not None for g in dgraphs):
                     def det_steps(count):
                         for st in lanes:
