@@ -88,3 +88,64 @@ def randomize_bn_stats(module, seed=7):
             m.weight.data.copy_(1.0 + 0.1 * torch.randn(m.weight.shape, generator=g))
             m.bias.data.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
     return module
+
+
+MAX_NUM_OBJ = 128   # lib/joint/dataset.py: padded ground-truth slots per scene
+NUM_CLASS = 18
+
+
+def make_labels(pc, seed, lang_num_max=8, max_obj=MAX_NUM_OBJ):
+    """Synthetic ground truth for a (B, N, 3 + C) batch in the layout the reference dataset yields
+    (lib/joint/dataset.py:780-830) and its losses read (lib/loss_helper/loss_detection.py, loss_grounding.py):
+    5-20 axis-aligned objects per scene centred on scene points, padded to `max_obj` slots; per-point votes
+    to the centre of the box a point lies in (vote_label repeats the single vote three times, mask 0/1);
+    `lang_num_max` sentence slots per scene, each referring to one object."""
+    rs = np.random.RandomState(seed)
+    xyz = pc[..., :3].numpy()
+    B, N = xyz.shape[:2]
+    out = {
+        "center_label": np.zeros((B, max_obj, 3), np.float32),
+        "heading_class_label": np.zeros((B, max_obj), np.int64),
+        "heading_residual_label": np.zeros((B, max_obj), np.float32),
+        "size_class_label": np.zeros((B, max_obj), np.int64),
+        "size_residual_label": np.zeros((B, max_obj, 3), np.float32),
+        "sem_cls_label": np.zeros((B, max_obj), np.int64),
+        "box_label_mask": np.zeros((B, max_obj), np.float32),
+        "vote_label": np.zeros((B, N, 9), np.float32),
+        "vote_label_mask": np.zeros((B, N), np.int64),
+        "ref_center_label_list": np.zeros((B, lang_num_max, 3), np.float32),
+        "ref_heading_class_label_list": np.zeros((B, lang_num_max), np.int64),
+        "ref_heading_residual_label_list": np.zeros((B, lang_num_max), np.float32),
+        "ref_size_class_label_list": np.zeros((B, lang_num_max), np.int64),
+        "ref_size_residual_label_list": np.zeros((B, lang_num_max, 3), np.float32),
+        "lang_num": np.zeros((B,), np.int64),
+    }
+    mean_size = mean_size_arr()
+    for b in range(B):
+        n_obj = int(rs.randint(5, 21))
+        centre = xyz[b, rs.choice(N, n_obj, replace=False)] + rs.normal(scale=0.05, size=(n_obj, 3)).astype(np.float32)
+        cls = rs.randint(0, NUM_CLASS, n_obj)
+        size = np.clip(mean_size[cls] + rs.normal(scale=0.05, size=(n_obj, 3)), 0.2, None).astype(np.float32)
+        out["center_label"][b, :n_obj] = centre
+        out["size_class_label"][b, :n_obj] = cls
+        out["size_residual_label"][b, :n_obj] = size - mean_size[cls]
+        out["sem_cls_label"][b, :n_obj] = cls
+        out["box_label_mask"][b, :n_obj] = 1
+        for i in range(n_obj):
+            inside = np.all(np.abs(xyz[b] - centre[i]) <= size[i] / 2, axis=1)
+            out["vote_label"][b, inside] = np.tile(centre[i] - xyz[b, inside], (1, 3))
+            out["vote_label_mask"][b, inside] = 1
+        n_lang = int(rs.randint(1, lang_num_max + 1))
+        ref = rs.randint(0, n_obj, n_lang)
+        out["lang_num"][b] = n_lang
+        out["ref_center_label_list"][b, :n_lang] = centre[ref]
+        out["ref_size_class_label_list"][b, :n_lang] = cls[ref]
+        out["ref_size_residual_label_list"][b, :n_lang] = size[ref] - mean_size[cls[ref]]
+    return {k: torch.from_numpy(v) for k, v in out.items()}
+
+
+def mean_size_arr():
+    """(18, 3) class mean box sizes (the reference loads them from a dataset file,
+    data/scannet/model_util_scannet.py:92; any fixed table serves a synthetic run)."""
+    rs = np.random.RandomState(7)
+    return rs.uniform(0.4, 1.6, size=(NUM_CLASS, 3)).astype(np.float32)

@@ -251,6 +251,98 @@ def reference_cuda_ext_leg(torch, pkg, model, dev_pool, steps):
                     "_ext (sm_100a build) + torch/cuDNN layers, same weights and inputs, 1 GPU"}
 
 
+def grounding_leg(torch, dist, pkg, syn, model, dev, dev_pool, host_pool, world, rank, steps=20):
+    """BASELINE configs[2]/[3] at N GPUs, forward: per rank 8 scenes -> detector (backbone + voting + proposal,
+    one CUDA-graph replay) -> detection losses (vote / objectness / box / semantic class, on nn_distance) ->
+    DIoU ("OID") reference loss -> OCC/OSC contrastive losses with the north star's ONE collective: the
+    L2-normalised object (8 x 256, 128) and sentence (8 x 8, 128) embeddings of every rank all-gathered in a
+    single NCCL call over NVLink.  The language branch is out of scope: sentence embeddings and the
+    matching head's logits are fixed synthetic tensors.  Returns a dict for the bench line (rank 0 prints)."""
+    import types
+    import numpy as np
+    LD = importlib.import_module("3dvlp_b200.loss_detection")
+    LG = importlib.import_module("3dvlp_b200.loss_grounding")
+    D = importlib.import_module("3dvlp_b200.dist")
+    L_MAX, K, H = 8, 256, 128
+    msa = syn.mean_size_arr()
+    det = pkg.VoteNetDetector(input_feature_dim=C_IN, mean_size_arr=msa)
+    det.backbone_net = model
+    torch.manual_seed(43)
+    syn.randomize_bn_stats(det.vgen); syn.randomize_bn_stats(det.proposal)
+    det = det.eval().to(dev)
+    cfg = types.SimpleNamespace(num_class=18, num_heading_bin=1, num_size_cluster=18, mean_size_arr=msa,
+                                mean_size_arr_tensor=torch.from_numpy(msa).to(dev))
+    torch.manual_seed(44)   # same projection weights on every rank (a data-parallel replica)
+    con = pkg.ContrastModule(cfg).to(dev)
+    labels = {k: v.to(dev) for k, v in syn.make_labels(host_pool[0], seed=100 + rank, lang_num_max=L_MAX).items()}
+    g = torch.Generator().manual_seed(200 + rank)
+    lang_emb = torch.randn(SCENES_PER_GPU * L_MAX, H, generator=g).to(dev)
+    cluster_ref = torch.randn(SCENES_PER_GPU * L_MAX, K, generator=g).to(dev)
+    graph = pkg.GraphedBackbone(det, dev_pool[0], throughput=False)
+
+    def step():
+        out = graph(dev_pool[0])
+        d = dict(out)
+        d.update(labels)
+        d.update({"epoch": 60, "istrain": 0, "random": 0.7, "lang_emb": lang_emb, "cluster_ref": cluster_ref,
+                  "bbox_feature": out["aggregated_vote_features"]})
+        d = LD.get_detection_loss(d, cfg)
+        d, ref_loss, _, _ = LG.compute_diou_loss(d, cfg)
+        d = con(d, gather=world > 1)
+        loss = d["vote_loss"] + 0.1 * d["objectness_loss"] + d["box_loss"] + 0.3 * ref_loss + d["diou_loss"] \
+            + d["lang_con_loss"] + d["iou_con_loss"]
+        return loss, d
+
+    with torch.no_grad():
+        for _ in range(3):
+            loss, d = step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss, d = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        # the collective alone, and its result against a plain list all_gather
+        obj = torch.nn.functional.normalize(con.pc_proj(d["bbox_feature"]), dim=-1).reshape(-1, H)
+        sent = torch.nn.functional.normalize(con.text_proj(lang_emb), dim=-1)
+        ag_us, equal = None, None
+        if world > 1:
+            for _ in range(5):
+                D.gather_contrastive_embeddings(obj, sent, normalize=False)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0.record()
+            for _ in range(50):
+                all_obj, all_sent = D.gather_contrastive_embeddings(obj, sent, normalize=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ag_us = e0.elapsed_time(e1) / 50 * 1e3
+            ref_o = [torch.empty_like(obj) for _ in range(world)]
+            ref_s = [torch.empty_like(sent) for _ in range(world)]
+            dist.all_gather(ref_o, obj.contiguous()); dist.all_gather(ref_s, sent.contiguous())
+            equal = bool(torch.equal(all_obj, torch.cat(ref_o)) and torch.equal(all_sent, torch.cat(ref_s)))
+        vals = torch.tensor([ms, ag_us or 0.0, float(loss), 1.0 if equal in (None, True) else 0.0], device=dev, dtype=torch.float64)
+        if world > 1:
+            mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            mn = vals.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            ms, ag_us, equal = float(mx[0]), float(mx[1]), bool(mn[3] > 0.5)
+    per_rank_bytes = (obj.numel() + sent.numel()) * 4
+    return {"value": SCENES_PER_GPU * world / (ms * 1e-3), "unit": "scenes/s", "ms_per_step": ms, "steps": steps,
+            "loss_rank0": float(loss), "lang_con_loss_rank0": float(d["lang_con_loss"]),
+            "all_gather": None if world == 1 else {
+                "us": ag_us, "bytes_sent_per_rank": per_rank_bytes, "bytes_received_per_rank": per_rank_bytes * world,
+                "tensors": "(%d,%d) object + (%d,%d) sentence embeddings, fp32, one all_gather_into_tensor" % (
+                    obj.shape[0], H, sent.shape[0], H),
+                "equals_reference_all_gather": equal, "nranks": world, "backend": "nccl"},
+            "what": "forward of BASELINE configs[2]: detector graph replay + vote/objectness/box/sem-cls losses + DIoU "
+                    "reference loss + OCC/OSC contrastive losses%s; eval-mode forward, one batch in flight, max over ranks" % (
+                        " with the cross-GPU embedding all-gather" if world > 1 else " (single GPU: no collective)")}
+
+
 def algorithmic_work():
     """Algorithmic bytes (HBM-bound ops) or FLOPs (tensor ops) per C-ABI call of one backbone forward on
     8 scenes x 40 000 points, C_in = 1 -- SURVEY.md section 8(d) / BASELINE.md section 4, keyed by
@@ -300,9 +392,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=20, help="batches in flight (graph replays on separate streams)")
-    ap.add_argument("--lane-priorities", type=int, default=1,
-                    help="1: the lanes (and the kernels of their graphs) get descending stream priorities, so batches in "
-                         "flight complete one after the other and their device->host reads overlap later compute")
+    ap.add_argument("--lane-priorities", type=int, default=-1,
+                    help="end-to-end leg: 1 = the lanes (and the kernels of their graphs) get descending stream "
+                         "priorities, so batches in flight complete one after the other and their device->host reads "
+                         "overlap later compute; 0 = equal priorities (all batches of a wave complete together); "
+                         "-1 (default) = 1 for a burst (steps < 4 x depth), 0 for a long run, where fair sharing "
+                         "already overlaps the reads of earlier steps")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -356,19 +451,20 @@ def main():
         least, greatest = torch.cuda.Stream.priority_range()
     except Exception:
         least, greatest = 0, -1
-    levels = least - greatest + 1 if args.lane_priorities else 1
+    stagger = args.lane_priorities == 1 or (args.lane_priorities < 0 and args.steps < 4 * depth)
+    levels = least - greatest + 1 if stagger else 1
 
     def lane_priority(k):
         return greatest + (k * levels) // depth if levels > 1 else 0
 
-    graphs = [pkg.GraphedBackbone(model, dev_pool[0], throughput=throughput_mode, priority=lane_priority(k))
-              for k in range(depth)]
-    lanes = [torch.cuda.Stream(device=dev, priority=lane_priority(k)) for k in range(depth)]
+    # device-resident leg: equal priorities (highest throughput: every sampling chain starts at once)
+    graphs = [pkg.GraphedBackbone(model, dev_pool[0], throughput=throughput_mode) for k in range(depth)]
+    lanes = [torch.cuda.Stream(device=dev) for k in range(depth)]
     graphed = graphs[0]
     execution = "cuda_graph" if graphed.graph is not None else "eager (graph capture failed: %s)" % graphed.capture_error
     main_stream = torch.cuda.current_stream(dev)
 
-    def run_steps(first, count, step_fn):
+    def run_steps(first, count, step_fn, graphs=graphs, lanes=lanes):
         """Issue `count` steps round-robin over the `depth` lanes; returns after joining them."""
         for st in lanes:
             st.wait_stream(main_stream)
@@ -409,25 +505,37 @@ def main():
     clk = clocks.stop()
 
     # ---------------- end to end through the public API with host buffers -------------------------
+    # A burst of K ~ depth steps under equal priorities completes all its batches together, so all the
+    # device->host reads queue up behind the last kernel; with descending lane priorities (kernels keep the
+    # priority of the stream their graph was captured on) batches complete one after the other and the reads
+    # of the early ones travel under the compute of the late ones (measured at K = 20: 16.1k -> 19.0k scenes/s)
+    if stagger:
+        e_graphs = [pkg.GraphedBackbone(model, dev_pool[0], throughput=throughput_mode, priority=lane_priority(k))
+                    for k in range(depth)]
+        e_lanes = [torch.cuda.Stream(device=dev, priority=lane_priority(k)) for k in range(depth)]
+    else:
+        e_graphs, e_lanes = graphs, lanes
     d = graphed(dev_pool[0])
     outs = ("fp2_features", "fp2_xyz", "fp2_inds")
     out_host = [{k: torch.empty(d[k].shape, dtype=d[k].dtype).pin_memory() for k in outs} for _ in range(depth)]
+    lane_of = {id(g): i for i, g in enumerate(e_graphs)}
 
     def e2e_step(g, s):
         r = g(host_pool[s % POOL])  # pinned host -> static device input, then the graph
         for k in outs:
-            out_host[graphs.index(g)][k].copy_(r[k], non_blocking=True)
+            out_host[lane_of[id(g)]][k].copy_(r[k], non_blocking=True)
 
-    run_steps(0, 3 * depth, e2e_step)   # untimed settling of the copy path (first use of the pinned buffers)
+    run_steps(0, 3 * depth, e2e_step, e_graphs, e_lanes)   # untimed settling of the copy path (first use of the pinned buffers)
     torch.cuda.synchronize()
-    run_steps(0, args.warmup, e2e_step)
+    run_steps(0, args.warmup, e2e_step, e_graphs, e_lanes)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    run_steps(args.warmup, args.steps, e2e_step)
+    run_steps(args.warmup, args.steps, e2e_step, e_graphs, e_lanes)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    graphs[0].check()  # raises if any kernel bailed out of a bounded wait during the timed regions
     h2d = dev_pool[0].numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in out_host[0].values())
 
@@ -436,19 +544,21 @@ def main():
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
+    try:  # every rank takes part (the leg contains the collective); rank 0 reports it
+        grounding = grounding_leg(torch, dist, pkg, syn, model, dev, dev_pool, host_pool, world, rank)
+    except Exception as ex:
+        if world > 1:
+            raise
+        grounding = {"error": repr(ex)[:300]}
     scenes = SCENES_PER_GPU * world * args.steps
     value = scenes / (ms * 1e-3)
     e2e_value = scenes / (ms_e2e * 1e-3)
 
     if rank == 0:
         hbm_peak, tensor_peak, peak_kind = peaks()
-        # profile the calls with the FPS variant the timed graphs captured
-        prev_opt = L.get_option("fps_bucket")
-        L.set_option("fps_bucket", 1 if throughput_mode else 0)
-        try:
+        # profile the calls under the SAME options the timed graphs captured (FPS variant, fused-SA grid)
+        with L.thread_options(**graphs[0].options):
             ops = per_op_profile(torch, L, model, dev_pool[1])
-        finally:
-            L.set_option("fps_bucket", prev_opt)
         step_ms = ms / args.steps
         # dominant kernel: the SA1 furthest-point sampling call (first FPS call of the forward)
         fps_key = next((k for k in ops if k[0].startswith("pn2_furthest_point_sampling") and k[1] == 0), None)
@@ -457,29 +567,37 @@ def main():
             t_fps = ops[fps_key] * 1e-3
             b = SCENES_PER_GPU
             bytes_alg = b * (12 * N_POINTS + 16 * 2048)  # xyz in, inds + new_xyz out
-            updates = b * N_POINTS * 2047
-            ach = bytes_alg / t_fps / 1e9
+            updates = b * N_POINTS * 2047                # N (m - 1) distance updates per scene ...
+            flops_alg = updates * 10                     # ... at 10 flop each (3 sub, mul, 2 fma, min, cmp)
+            fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.5 TFLOP/s: SURVEY 8(d)'s third denominator
             traffic = None
-            tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+            tp = os.path.join(ROOT, "profiles", "traffic_r02.json")
+            if not os.path.exists(tp):
+                tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
             if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
                 traffic = json.load(open(tp)).get(
                     "fps_bucket_kernel_sa1_bytes_per_launch" if throughput_mode else "fps_kernel_sa1_bytes_per_launch")
+            ach = flops_alg / t_fps / 1e12
+            # FPS is bound by fp32 issue + the latency of its dependent rounds, not by HBM or the tensor pipe
+            # (SURVEY 8(d)): the fraction is algorithmic flops over the fp32 FMA peak of the whole GPU.  The
+            # bucketed kernel prunes most of the algorithmic updates, so this is work-equivalent throughput,
+            # not a pipe utilisation (ncu: profiles/fps_bucket_r02.txt).
             roofline = {"kernel": ("fps_bucket_kernel" if throughput_mode else "fps_kernel") + " (SA1, 40000->2048)",
-                        "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                        "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
-                        "ms": ops[fps_key], "share_of_forward": ops[fps_key] / sum(ops.values()),
-                        "note": "FPS is latency/ALU-bound by construction (2047 dependent rounds); see alu_frac",
-                        "alu_gflops": updates * 10 / t_fps / 1e9, "alu_frac": updates * 10 / t_fps / 74.5e12,
-                        "us_per_sample": ops[fps_key] * 1e3 / 2047}
-            # the kernel holds 1 SM per scene (bucketed) or a 16-CTA cluster per scene: the fp32 rate of the
-            # algorithmic updates against the peak of the SMs it actually occupies (pruning in the bucketed
-            # kernel executes fewer updates than the algorithm counts, so this can approach or pass 1)
-            sms = SCENES_PER_GPU * (1 if throughput_mode else 16)
-            roofline["sms_occupied"] = sms
-            roofline["alu_frac_of_occupied_sms"] = roofline["alu_frac"] * 148.0 / sms
+                        "bound": "fp32-alu/latency", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                        "frac": ach / fp32_peak, "traffic": traffic,
+                        "peak_kind": "148 SM x 128 lanes x 2 flop x 1.965 GHz (SURVEY 8d)",
+                        "ms": ops[fps_key], "share_of_serialised_forward": ops[fps_key] / sum(ops.values()),
+                        "us_per_sample": ops[fps_key] * 1e3 / 2047,
+                        "step_level_frac": flops_alg / (step_ms * 1e-3) / 1e12 / fp32_peak,
+                        "hbm_note": {"algorithmic_bytes": bytes_alg, "achieved_gbs": bytes_alg / t_fps / 1e9,
+                                     "peak_gbs": hbm_peak, "frac": bytes_alg / t_fps / 1e9 / hbm_peak, "peak_kind": peak_kind},
+                        "sms_occupied": SCENES_PER_GPU * (1 if throughput_mode else 16),
+                        "note": "timed alone with CUDA events around the C-ABI call (one launch, eager, same options as "
+                                "the captured graphs); in the timed region ~6 of these run concurrently with other batches' "
+                                "kernels, which is what step_level_frac accounts for"}
         work = algorithmic_work()
         for (name, k), v in sorted(ops.items(), key=lambda kv: -kv[1]):
-            row = {"call": name, "nth": k, "ms": round(v, 4), "share_of_forward": round(v / sum(ops.values()), 4)}
+            row = {"call": name, "nth": k, "ms": round(v, 4), "share_of_serialised_forward": round(v / sum(ops.values()), 4)}
             w = work.get((name, k))
             if w:
                 bound, amount = w
@@ -501,11 +619,16 @@ def main():
                     "c_in": C_IN, "l2": "rotating pool of %d input batches (%.0f MB > L2)" % (
                         POOL, POOL * SCENES_PER_GPU * N_POINTS * 4 * (3 + C_IN) / 1e6),
                     "parallelism": "scene-sharded dp%d, no data-path collective" % world,
-                    "execution": execution, "batches_in_flight": depth, "lane_priority_levels": levels,
+                    "execution": execution, "batches_in_flight": depth,
+                    "e2e_lane_priority_levels": levels,
                     "fps_algorithm": "bucketed single-SM (throughput mode)" if throughput_mode else "16-CTA cluster (latency mode)"},
                 "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_ops": roofline_ops[:24]}
+                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_ops": roofline_ops[:24],
+                "roofline_ops_note": "per C-ABI call, timed alone (eager, CUDA events, median of 5) under the options the "
+                                     "timed graphs captured (%s); shares are of the SERIALISED per-op sum, not of the "
+                                     "pipelined step" % json.dumps(graphs[0].options)}
+        line["grounding_step_forward"] = grounding
         if world == 1:
             try:
                 line["ref_cuda_ext"] = reference_cuda_ext_leg(torch, pkg, model, dev_pool, min(args.steps, 5))
@@ -532,7 +655,7 @@ def main():
                                              "what": "backbone + VotingModule + L2 norm + vote aggregation (256 clusters), "
                                                      "eager, one batch in flight"}
                 # the same front end the way the backbone is measured: CUDA-graph replays, `depth` batches in flight
-                fgraphs = [pkg.GraphedBackbone(fe, dev_pool[0], throughput=throughput_mode, priority=lane_priority(k)) for k in range(depth)]
+                fgraphs = [pkg.GraphedBackbone(fe, dev_pool[0], throughput=throughput_mode) for k in range(depth)]
                 if all(g.graph is not None for g in fgraphs):
                     def fe_steps(count):
                         for st in lanes:
@@ -562,7 +685,7 @@ def main():
                 det.proposal.vote_aggregation = fe.proposal.vote_aggregation
                 syn.randomize_bn_stats(det.proposal.proposal)
                 det = det.eval().to(dev)
-                dgraphs = [pkg.GraphedBackbone(det, dev_pool[0], throughput=throughput_mode, priority=lane_priority(k)) for k in range(depth)]
+                dgraphs = [pkg.GraphedBackbone(det, dev_pool[0], throughput=throughput_mode) for k in range(depth)]
                 if all(g.graph is not None for g in dgraphs):
                     def det_steps(count):
                         for st in lanes:
@@ -586,6 +709,23 @@ def main():
                 del dgraphs
             except Exception as ex:
                 line["votenet_detector"] = {"error": repr(ex)[:200]}
+        if world == 1 and not args.no_cpu_baseline:
+            try:  # achieved error of the captured graph at the bench configuration, one scene against the oracle
+                from oracle import oracle as O
+                sd0 = {k: v.cpu() for k, v in model.state_dict().items()}
+                got = graphs[0](dev_pool[0])
+                torch.cuda.synchronize()
+                want = O.backbone(host_pool[0, :1].clone(), sd0)
+                num = {"scene": "batch 0, scene 0 (checker: oracle.backbone, fp32 reference semantics)"}
+                for k in ("sa1_inds", "sa2_inds", "fp2_inds", "sa1_xyz", "sa2_xyz", "sa3_xyz", "sa4_xyz"):
+                    num[k + "_bit_exact"] = bool(torch.equal(got[k][:1].cpu(), want[k]))
+                for k in ("sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features"):
+                    a, w = got[k][:1].float().cpu(), want[k]
+                    num[k + "_max_norm_err"] = float((a - w).abs().max() / w.abs().max())
+                    num[k + "_rel_rms_err"] = float((a - w).pow(2).mean().sqrt() / w.pow(2).mean().sqrt())
+                line["numerics"] = num
+            except Exception as ex:
+                line["numerics"] = {"error": repr(ex)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             cores = os.cpu_count() or 1
