@@ -16,8 +16,9 @@ import sys as _sys
 
 from . import _lib  # noqa: F401
 from ._lib import get_option, get_stat, set_option, set_option_thread, thread_options  # noqa: F401
-from . import _ext, backbone, nn_distance as _nn_distance_mod, pointnet2_modules, pointnet2_utils, pytorch_utils, voting, loss_detection, box_util, loss_grounding, contrast, proposal  # noqa: F401
+from . import _ext, backbone, mlp_train, nn_distance as _nn_distance_mod, pointnet2_modules, pointnet2_utils, pytorch_utils, voting, loss_detection, box_util, loss_grounding, contrast, proposal  # noqa: F401
 from .backbone import Pointnet2Backbone  # noqa: F401
+from .mlp_train import mlp_backend  # noqa: F401
 from .graph import GraphedBackbone  # noqa: F401
 from .nn_distance import huber_loss, knn_distance, nn_distance  # noqa: F401
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes  # noqa: F401

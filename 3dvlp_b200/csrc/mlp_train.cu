@@ -1,0 +1,507 @@
+// Training-mode SharedMLP (+ max-pool) on own kernels: batch-statistics BatchNorm, backward, weight gradients.
+//
+// Reference: pytorch_utils.py:11-36 (SharedMLP = per layer Conv2d 1x1 without bias -> BatchNorm2d -> ReLU),
+// pointnet2_modules.py:251-257 (max_pool2d over nsample), executed by cuDNN in train() mode with batch
+// statistics over all (B, npoint, nsample) positions (lib/joint/solver_3dvlp.py:580-584).
+//
+// Layout: activations are point-major rows, (P, C) with P = B * npoint * nsample positions.
+//   forward, per layer   Y = X W^T on tcgen05 (pn2_linear_bf16: bf16 operands, fp32 accumulate, Y kept in fp32)
+//                        pn2_column_stats      per-channel sum / sum of squares of Y, accumulated in double
+//                        pn2_bn_finalize       mean, biased variance -> scale / shift; running statistics
+//                        pn2_bn_relu_rows      X' = bf16(relu(Y scale + shift))          (hidden layers)
+//                        pn2_bn_relu_maxpool   out[b,c,j] = max_s relu(Y scale + shift)  (last layer) + arg-max slot
+//   backward, per layer  pn2_bn_bwd_stats      s1 = sum dYhat, s2 = sum dYhat xhat  (dYhat = upstream masked by ReLU;
+//                                              the last layer's upstream is the pooled gradient at the arg-max slot)
+//                        pn2_bn_bwd_rows       dY = gamma invstd (dYhat - s1/P - xhat s2/P)  -> bf16 rows
+//                        pn2_wgrad_bf16        dW = dY^T X on tcgen05: operands are transposed on the way into
+//                                              shared memory, split over K = P across persistent CTAs
+//                        pn2_linear_bf16       dX = dY W (the same linear kernel, W^T packed as its weight)
+//   pn2_unpack_rows      (P, ld) fp32 rows -> the reference's (B, C, n) layout (gradient w.r.t. the grouped tensor)
+#include "tc.cuh"
+
+namespace pn2 {
+namespace {
+
+constexpr int RT = 256;  // threads of the reduction / elementwise kernels
+
+// ---- per-channel reductions over rows: thread = (row lane, channel), fp32 partials per thread over a
+// bounded row range, shared-memory combine over the row lanes, ONE double atomic per channel per CTA ----
+template <typename F>
+__device__ __forceinline__ void column_reduce2(long long rows, int c, long long rows_per_cta, F f, double* o1, double* o2) {
+  __shared__ float s_a[RT], s_b[RT];
+  const int lanes = RT / c;                    // row lanes per CTA (c <= RT)
+  const int tx = threadIdx.x % c, ty = threadIdx.x / c;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+  float a = 0.f, b = 0.f;
+  if (ty < lanes) {
+    for (long long r = r0 + ty; r < r1; r += lanes) {
+      float va, vb;
+      f(r, tx, va, vb);
+      a += va; b += vb;
+    }
+  }
+  s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
+  __syncthreads();
+  if (ty == 0) {
+    double da = 0.0, db = 0.0;
+    for (int l = 0; l < lanes; ++l) { da += s_a[l * c + tx]; db += s_b[l * c + tx]; }
+    atomicAdd(o1 + tx, da);
+    atomicAdd(o2 + tx, db);
+  }
+}
+
+__global__ void __launch_bounds__(RT)
+column_stats_kernel(long long rows, int c, int ld, long long rows_per_cta, const float* __restrict__ y,
+                    double* __restrict__ sum, double* __restrict__ sumsq) {
+  column_reduce2(rows, c, rows_per_cta, [&](long long r, int ch, float& a, float& b) {
+    const float v = __ldg(y + r * ld + ch);
+    a = v; b = v * v;
+  }, sum, sumsq);
+}
+
+__global__ void bn_finalize_kernel(int c, double count, const double* __restrict__ sum, const double* __restrict__ sumsq,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double mean = sum[ch] / count;
+  double var = sumsq[ch] / count - mean * mean;  // biased (what normalisation uses)
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float g = gamma ? gamma[ch] : 1.f, bt = beta ? beta[ch] : 0.f;
+  scale[ch] = g * invstd;
+  shift[ch] = bt - static_cast<float>(mean) * g * invstd;
+  mean_out[ch] = static_cast<float>(mean);
+  invstd_out[ch] = invstd;
+  if (running_mean) {  // torch.nn.BatchNorm: running_var takes the UNBIASED batch variance
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * static_cast<float>(mean);
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+// eval-mode statistics (gradients through a frozen BatchNorm): scale / shift from the running buffers
+__global__ void bn_frozen_kernel(int c, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                 float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                 float* __restrict__ invstd_out) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const float invstd = 1.f / sqrtf(running_var[ch] + eps);
+  const float g = gamma ? gamma[ch] : 1.f, bt = beta ? beta[ch] : 0.f;
+  scale[ch] = g * invstd;
+  shift[ch] = bt - running_mean[ch] * g * invstd;
+  mean_out[ch] = running_mean[ch];
+  invstd_out[ch] = invstd;
+}
+
+// X' = bf16(relu(Y * scale + shift)), thread = 8 channels of one row (one 16-byte store)
+__global__ void __launch_bounds__(RT)
+bn_relu_rows_kernel(long long rows, int c, int ld, const float* __restrict__ y, const float* __restrict__ scale,
+                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ x) {
+  const int chunks = c >> 3;
+  const long long t = static_cast<long long>(blockIdx.x) * RT + threadIdx.x;
+  if (t >= rows * chunks) return;
+  const long long r = t / chunks;
+  const int ch0 = static_cast<int>(t - r * chunks) << 3;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(y + r * ld + ch0));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(y + r * ld + ch0) + 1);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = __fmaf_rn(v[i], __ldg(scale + ch0 + i), __ldg(shift + ch0 + i));
+  *reinterpret_cast<uint4*>(x + r * c + ch0) = make_uint4(tc::pack_bf16_relu(o[0], o[1]), tc::pack_bf16_relu(o[2], o[3]),
+                                                          tc::pack_bf16_relu(o[4], o[5]), tc::pack_bf16_relu(o[6], o[7]));
+}
+
+// out[b, ch, j] = max over the ns rows of group g = b * npoint + j of relu(y * scale + shift); arg-max = the FIRST
+// slot that attains it (F.max_pool2d: strict '>' scan)
+__global__ void __launch_bounds__(RT)
+bn_relu_maxpool_kernel(int groups, int ns, int c, int ld, int npoint, const float* __restrict__ y,
+                       const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out_cm,
+                       int* __restrict__ argmax) {
+  const long long t = static_cast<long long>(blockIdx.x) * RT + threadIdx.x;
+  if (t >= static_cast<long long>(groups) * c) return;
+  const int g = static_cast<int>(t / c), ch = static_cast<int>(t - static_cast<long long>(g) * c);
+  const float sc = __ldg(scale + ch), sh = __ldg(shift + ch);
+  const float* row = y + static_cast<long long>(g) * ns * ld + ch;
+  float best = -INFINITY;
+  int bi = 0;
+  for (int s = 0; s < ns; ++s) {
+    const float v = fmaxf(__fmaf_rn(__ldg(row + static_cast<long long>(s) * ld), sc, sh), 0.f);
+    if (s == 0 || v > best) { best = v; bi = s; }
+  }
+  const int b = g / npoint, j = g - b * npoint;
+  const long long o = (static_cast<long long>(b) * c + ch) * npoint + j;
+  out_cm[o] = best;
+  argmax[o] = bi;
+}
+
+// ---- backward ----------------------------------------------------------------------------------------
+// dense upstream: dYhat = dA * [relu input > 0]
+__global__ void __launch_bounds__(RT)
+bn_bwd_stats_dense_kernel(long long rows, int c, int ld_da, int ld_y, long long rows_per_cta, const float* __restrict__ da,
+                          const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ s1,
+                          double* __restrict__ s2) {
+  column_reduce2(rows, c, rows_per_cta, [&](long long r, int ch, float& a, float& b) {
+    const float yv = __ldg(y + r * ld_y + ch);
+    const float act = __fmaf_rn(yv, __ldg(scale + ch), __ldg(shift + ch));
+    const float d = act > 0.f ? __ldg(da + r * ld_da + ch) : 0.f;
+    a = d; b = d * (yv - __ldg(mean + ch)) * __ldg(invstd + ch);
+  }, s1, s2);
+}
+
+// pooled upstream: the gradient of group g reaches only its arg-max row; "rows" of the reduction are groups
+__global__ void __launch_bounds__(RT)
+bn_bwd_stats_pool_kernel(long long groups, int ns, int c, int ld_y, int npoint, long long groups_per_cta,
+                         const float* __restrict__ dout_cm, const int* __restrict__ argmax, const float* __restrict__ y,
+                         const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, double* __restrict__ s1, double* __restrict__ s2) {
+  column_reduce2(groups, c, groups_per_cta, [&](long long g, int ch, float& a, float& b) {
+    const long long bb = g / npoint, j = g - bb * npoint;
+    const long long o = (bb * c + ch) * npoint + j;
+    const long long r = g * ns + __ldg(argmax + o);
+    const float yv = __ldg(y + r * ld_y + ch);
+    const float act = __fmaf_rn(yv, __ldg(scale + ch), __ldg(shift + ch));
+    const float d = act > 0.f ? __ldg(dout_cm + o) : 0.f;
+    a = d; b = d * (yv - __ldg(mean + ch)) * __ldg(invstd + ch);
+  }, s1, s2);
+}
+
+// dY = gamma invstd (dYhat - (s1 + xhat s2) / count)  [count > 0: batch statistics]  or  gamma invstd dYhat
+// [count == 0: frozen statistics] -> bf16 rows.  Upstream dense (da) or pooled (dout_cm + argmax).
+__global__ void __launch_bounds__(RT)
+bn_bwd_rows_kernel(long long rows, int c, int ld_da, int ld_y, const float* __restrict__ da,
+                   const float* __restrict__ dout_cm, const int* __restrict__ argmax, int ns, int npoint,
+                   const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                   const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                   const double* __restrict__ s1, const double* __restrict__ s2, double count,
+                   __nv_bfloat16* __restrict__ dy) {
+  const int chunks = c >> 3;
+  const long long t = static_cast<long long>(blockIdx.x) * RT + threadIdx.x;
+  if (t >= rows * chunks) return;
+  const long long r = t / chunks;
+  const int ch0 = static_cast<int>(t - r * chunks) << 3;
+  const float inv_count = count > 0.0 ? static_cast<float>(1.0 / count) : 0.f;
+  long long g = 0, bb = 0, j = 0;
+  int slot = 0;
+  if (!da) { g = r / ns; slot = static_cast<int>(r - g * ns); bb = g / npoint; j = g - bb * npoint; }
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = ch0 + i;
+    const float yv = __ldg(y + r * ld_y + ch);
+    const float act = __fmaf_rn(yv, __ldg(scale + ch), __ldg(shift + ch));
+    float up;
+    if (da) {
+      up = __ldg(da + r * ld_da + ch);
+    } else {
+      const long long oo = (bb * c + ch) * npoint + j;
+      up = __ldg(argmax + oo) == slot ? __ldg(dout_cm + oo) : 0.f;
+    }
+    const float d = act > 0.f ? up : 0.f;
+    const float is = __ldg(invstd + ch);
+    const float xhat = (yv - __ldg(mean + ch)) * is;
+    const float corr = (static_cast<float>(s1[ch]) + xhat * static_cast<float>(s2[ch])) * inv_count;
+    o[i] = (gamma ? __ldg(gamma + ch) : 1.f) * is * (d - corr);
+  }
+  *reinterpret_cast<uint4*>(dy + r * c + ch0) = make_uint4(tc::pack_bf16(o[0], o[1]), tc::pack_bf16(o[2], o[3]),
+                                                           tc::pack_bf16(o[4], o[5]), tc::pack_bf16(o[6], o[7]));
+}
+
+// (b * n, ld) fp32 rows, columns [0, c) -> (b, c, n) slices of a channel-major tensor with batch stride `bstride`
+__global__ void __launch_bounds__(256)
+unpack_rows_kernel(int c, int n, int ld, long long bstride, const float* __restrict__ rows, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, ch = c0 + tx;
+    tile[i][tx] = (p < n && ch < c) ? __ldg(rows + (static_cast<long long>(b) * n + p) * ld + ch) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int ch = c0 + i, p = p0 + tx;
+    if (ch < c && p < n) out[static_cast<long long>(b) * bstride + static_cast<long long>(ch) * n + p] = tile[tx][i];
+  }
+}
+
+// ---- weight gradient: dW[co][ci] += sum_p dY[p][co] * X[p][ci] on tcgen05 -----------------------------
+// Both operands arrive as point-major rows, i.e. with the contraction index p as the SLOW dimension; the MMA
+// wants K-major tiles.  A thread loads 8 channels of two consecutive positions (two 16-byte loads), pairs them
+// per channel and writes eight 32-bit words into the SWIZZLE_128B K-major image (row = channel, k = position).
+// CTA = one [128 x NT] block of dW (A rows = 128 output channels, zero rows beyond c_out) over a slice of P;
+// 64 positions per step, two shared-memory stages, accumulator in TMEM, fp32 atomics into dW at the end.
+constexpr int WG_THREADS = 128;
+
+struct WgArgs {
+  const __nv_bfloat16* dy;  // (rows, c_out)
+  const __nv_bfloat16* x;   // (rows, ld_x)
+  float* dw;                // (c_out, c_in)
+  int* err;
+  long long rows;
+  int c_out, c_in, ld_x, nt;  // nt = columns of this launch's N tile (multiple of 16, <= 256)
+  long long chunks_per_cta;
+};
+
+__device__ __forceinline__ void wg_store_tile(uint32_t smem_tile, const __nv_bfloat16* __restrict__ src, int ld,
+                                              long long row0, long long rows, int ch0, int ch_count, int tile_rows,
+                                              int tid) {
+  // tile_rows channels x 64 positions; items = (position pair, 8-channel group).  A warp covers 16 position
+  // pairs x 2 adjacent channel groups: every 16-byte load is half of a fully used 32-byte sector, and the
+  // shared-memory words of lanes with different position pairs fall into different banks (the bank is a function
+  // of k = 2 pp under the 128-byte swizzle), leaving a 2-way conflict between the two channel groups.
+  const int groups = tile_rows >> 3;  // even: tile_rows is a multiple of 16
+  for (int it = tid; it < 32 * groups; it += WG_THREADS) {
+    const int pp = (it >> 1) & 31, cg = ((it >> 6) << 1) | (it & 1);
+    const long long p = row0 + 2 * pp;
+    const int c = ch0 + cg * 8;
+    uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
+    if (cg * 8 < ch_count) {  // ch_count is a multiple of 8
+      if (p < rows) lo = __ldg(reinterpret_cast<const uint4*>(src + p * ld + c));
+      if (p + 1 < rows) hi = __ldg(reinterpret_cast<const uint4*>(src + (p + 1) * ld + c));
+    }
+    const uint32_t l[4] = {lo.x, lo.y, lo.z, lo.w}, h[4] = {hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // channels 2e, 2e+1 of the group: word = (value at p) | (value at p+1) << 16
+      const uint32_t w0 = (l[e] & 0xffffu) | (h[e] << 16);
+      const uint32_t w1 = (l[e] >> 16) | (h[e] & 0xffff0000u);
+      const uint32_t r0 = cg * 8 + 2 * e, r1 = r0 + 1;
+      const uint32_t k = 2 * pp;  // even: 4-byte aligned inside its 16-byte chunk
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_tile + tc::swz_off(r0, k >> 3) + (k & 7) * 2), "r"(w0) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_tile + tc::swz_off(r1, k >> 3) + (k & 7) * 2), "r"(w1) : "memory");
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_mma[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = 128u * 128u, b_bytes = static_cast<uint32_t>(a.nt) * 128u;
+  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
+  const int co0 = blockIdx.y * 128, ci0 = blockIdx.z * 256;
+  const int co_cnt = min(128, a.c_out - co0);                 // multiple of 8
+  const int ci_cnt = min(a.nt, ((a.c_in - ci0) + 7) & ~7);      // channels with data (x rows are padded to ld_x)
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(a.nt)) tmem_cols <<= 1;
+  if (tid == 0) {
+    mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1);
+    fence_mbar_init_cluster();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_d = tmem_slot;
+  const uint32_t idesc = tc::idesc_bf16_f32(128, a.nt);
+  const long long total_chunks = (a.rows + 63) / 64;
+  const long long c_first = static_cast<long long>(blockIdx.x) * a.chunks_per_cta;
+  long long c_last = c_first + a.chunks_per_cta;
+  if (c_last > total_chunks) c_last = total_chunks;
+  bool failed = false;
+  int n_issued = 0;
+  for (long long ck = c_first; ck < c_last && !failed; ++ck, ++n_issued) {
+    const int s = n_issued & 1;
+    // stage s was last read by the MMAs issued two steps ago
+    if (n_issued >= 2 && !mbar_wait(&bar_mma[s], ((n_issued - 2) >> 1) & 1)) { failed = true; break; }
+    const uint32_t sa = base + s * stage_bytes;
+    wg_store_tile(sa, a.dy, a.c_out, ck * 64, a.rows, co0, co_cnt, 128, tid);
+    wg_store_tile(sa + a_bytes, a.x, a.ld_x, ck * 64, a.rows, ci0, ci_cnt, a.nt, tid);
+    fence_proxy_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        tc::mma_bf16(tmem_d, tc::smem_desc_sw128(sa + kk * 32), tc::smem_desc_sw128(sa + a_bytes + kk * 32), idesc,
+                     (n_issued > 0 || kk > 0) ? 1u : 0u);
+      tc::mma_commit(&bar_mma[s]);
+    }
+  }
+  if (!failed && n_issued > 0) {
+    const int last = n_issued - 1;
+    if (!mbar_wait(&bar_mma[last & 1], (last >> 1) & 1)) failed = true;
+    // the other stage's commit completed earlier (commits complete in order)
+  }
+  if (failed) {
+    if (tid == 0) atomicExch(a.err, 2);
+  } else if (n_issued > 0) {
+    tc::fence_after_sync();
+    const int co = co0 + tid;  // thread = TMEM lane = output channel
+    const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int c0 = 0; c0 < a.nt; c0 += 16) {
+      float v[16];
+      tc::tmem_ld16(lane_base + c0, v);
+      if (co < a.c_out) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int ci = ci0 + c0 + i;
+          if (ci < a.c_in) atomicAdd(a.dw + static_cast<long long>(co) * a.c_in + ci, v[i]);
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
+}
+
+long long pick_rows_per_cta(long long rows, int c) {
+  // enough CTAs to fill the machine, at most ~4096 values per thread partial (fp32 accumulation error)
+  const long long lanes = RT / c > 0 ? RT / c : 1;
+  long long per = (rows + 8LL * sm_count() - 1) / (8LL * sm_count());
+  const long long cap = 4096 * lanes;
+  if (per > cap) per = cap;
+  if (per < lanes) per = lanes;
+  return per;
+}
+
+}  // namespace
+
+int* device_err_flag();
+
+}  // namespace pn2
+
+using namespace pn2;
+
+extern "C" int pn2_column_stats(long long rows, int c, int ld, const float* y, double* sum, double* sumsq, void* stream) {
+  PN2_RANGE("pn2_column_stats");
+  if (rows <= 0) return PN2_OK;
+  PN2_REQUIRE(c > 0 && c <= RT && ld >= c && y && sum && sumsq, "column_stats: bad arguments (c=%d must be <= %d)", c, RT);
+  const long long per = pick_rows_per_cta(rows, c);
+  const long long grid = (rows + per - 1) / per;
+  column_stats_kernel<<<static_cast<unsigned>(grid), RT, 0, as_stream(stream)>>>(rows, c, ld, per, y, sum, sumsq);
+  PN2_CHECK_LAUNCH("column_stats_kernel");
+  return PN2_OK;
+}
+
+extern "C" int pn2_bn_finalize(int c, long long count, const double* sum, const double* sumsq, const float* gamma,
+                               const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                               float* scale, float* shift, float* mean, float* invstd, void* stream) {
+  PN2_RANGE("pn2_bn_finalize");
+  PN2_REQUIRE(c > 0 && scale && shift && mean && invstd, "bn_finalize: bad arguments");
+  if (count > 0) {
+    PN2_REQUIRE(sum && sumsq, "bn_finalize: batch statistics need sum / sumsq");
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(c, static_cast<double>(count), sum, sumsq, gamma, beta,
+                                                                        eps, momentum, running_mean, running_var, scale, shift,
+                                                                        mean, invstd);
+  } else {  // count == 0: frozen (eval-mode) statistics from the running buffers
+    PN2_REQUIRE(running_mean && running_var, "bn_finalize: frozen statistics need the running buffers");
+    bn_frozen_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(c, gamma, beta, eps, running_mean, running_var, scale,
+                                                                      shift, mean, invstd);
+  }
+  PN2_CHECK_LAUNCH("bn_finalize_kernel");
+  return PN2_OK;
+}
+
+extern "C" int pn2_bn_relu_rows(long long rows, int c, int ld, const float* y, const float* scale, const float* shift,
+                                void* x_bf16, void* stream) {
+  PN2_RANGE("pn2_bn_relu_rows");
+  if (rows <= 0) return PN2_OK;
+  PN2_REQUIRE(c > 0 && c % 8 == 0 && ld >= c && ld % 4 == 0 && y && scale && shift && x_bf16, "bn_relu_rows: bad arguments");
+  const long long total = rows * (c / 8);
+  bn_relu_rows_kernel<<<static_cast<unsigned>((total + RT - 1) / RT), RT, 0, as_stream(stream)>>>(
+      rows, c, ld, y, scale, shift, static_cast<__nv_bfloat16*>(x_bf16));
+  PN2_CHECK_LAUNCH("bn_relu_rows_kernel");
+  return PN2_OK;
+}
+
+extern "C" int pn2_bn_relu_maxpool(int groups, int ns, int c, int ld, int npoint, const float* y, const float* scale,
+                                   const float* shift, float* out_cm, int* argmax, void* stream) {
+  PN2_RANGE("pn2_bn_relu_maxpool");
+  if (groups <= 0) return PN2_OK;
+  PN2_REQUIRE(ns > 0 && c > 0 && ld >= c && npoint > 0 && groups % npoint == 0 && y && scale && shift && out_cm && argmax,
+              "bn_relu_maxpool: bad arguments");
+  const long long total = static_cast<long long>(groups) * c;
+  bn_relu_maxpool_kernel<<<static_cast<unsigned>((total + RT - 1) / RT), RT, 0, as_stream(stream)>>>(
+      groups, ns, c, ld, npoint, y, scale, shift, out_cm, argmax);
+  PN2_CHECK_LAUNCH("bn_relu_maxpool_kernel");
+  return PN2_OK;
+}
+
+extern "C" int pn2_bn_bwd_stats(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_cm,
+                                const int* argmax, int ns, int npoint, const float* y, const float* scale,
+                                const float* shift, const float* mean, const float* invstd, double* s1, double* s2,
+                                void* stream) {
+  PN2_RANGE("pn2_bn_bwd_stats");
+  if (rows <= 0) return PN2_OK;
+  PN2_REQUIRE(c > 0 && c <= RT && y && scale && shift && mean && invstd && s1 && s2, "bn_bwd_stats: bad arguments");
+  if (da) {
+    const long long per = pick_rows_per_cta(rows, c);
+    bn_bwd_stats_dense_kernel<<<static_cast<unsigned>((rows + per - 1) / per), RT, 0, as_stream(stream)>>>(
+        rows, c, ld_da, ld_y, per, da, y, scale, shift, mean, invstd, s1, s2);
+  } else {
+    PN2_REQUIRE(dout_cm && argmax && ns > 0 && npoint > 0 && rows % ns == 0, "bn_bwd_stats: pooled upstream needs dout / argmax");
+    const long long groups = rows / ns;
+    const long long per = pick_rows_per_cta(groups, c);
+    bn_bwd_stats_pool_kernel<<<static_cast<unsigned>((groups + per - 1) / per), RT, 0, as_stream(stream)>>>(
+        groups, ns, c, ld_y, npoint, per, dout_cm, argmax, y, scale, shift, mean, invstd, s1, s2);
+  }
+  PN2_CHECK_LAUNCH("bn_bwd_stats_kernel");
+  return PN2_OK;
+}
+
+extern "C" int pn2_bn_bwd_rows(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_cm,
+                               const int* argmax, int ns, int npoint, const float* y, const float* scale,
+                               const float* shift, const float* mean, const float* invstd, const float* gamma,
+                               const double* s1, const double* s2, long long count, void* dy_bf16, void* stream) {
+  PN2_RANGE("pn2_bn_bwd_rows");
+  if (rows <= 0) return PN2_OK;
+  PN2_REQUIRE(c > 0 && c % 8 == 0 && y && scale && shift && mean && invstd && s1 && s2 && dy_bf16, "bn_bwd_rows: bad arguments");
+  PN2_REQUIRE(da || (dout_cm && argmax && ns > 0 && npoint > 0), "bn_bwd_rows: no upstream gradient");
+  const long long total = rows * (c / 8);
+  bn_bwd_rows_kernel<<<static_cast<unsigned>((total + RT - 1) / RT), RT, 0, as_stream(stream)>>>(
+      rows, c, ld_da, ld_y, da, dout_cm, argmax, ns, npoint, y, scale, shift, mean, invstd, gamma, s1, s2,
+      static_cast<double>(count), static_cast<__nv_bfloat16*>(dy_bf16));
+  PN2_CHECK_LAUNCH("bn_bwd_rows_kernel");
+  return PN2_OK;
+}
+
+extern "C" int pn2_unpack_rows(int b, int c, int n, int ld, long long batch_stride, const float* rows, float* out,
+                               void* stream) {
+  PN2_RANGE("pn2_unpack_rows");
+  if (b <= 0 || c <= 0 || n <= 0) return PN2_OK;
+  PN2_REQUIRE(ld >= c && rows && out && b <= 65535 && batch_stride >= static_cast<long long>(c) * n, "unpack_rows: bad arguments");
+  dim3 grid((n + 31) / 32, (c + 31) / 32, b);
+  unpack_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(c, n, ld, batch_stride, rows, out);
+  PN2_CHECK_LAUNCH("unpack_rows_kernel");
+  return PN2_OK;
+}
+
+extern "C" int pn2_wgrad_bf16(long long rows, int c_out, int c_in, int ld_x, const void* dy_bf16, const void* x_bf16,
+                              float* dw, void* stream) {
+  PN2_RANGE("pn2_wgrad_bf16");
+  if (rows <= 0) return PN2_OK;
+  PN2_REQUIRE(c_out > 0 && c_out % 8 == 0 && c_in > 0 && ld_x % 8 == 0 && ld_x >= ((c_in + 7) & ~7) && dy_bf16 && x_bf16 && dw,
+              "wgrad_bf16: bad arguments (c_out %% 8, ld_x %% 8, ld_x >= c_in rounded up to 8)");
+  WgArgs a;
+  a.dy = static_cast<const __nv_bfloat16*>(dy_bf16); a.x = static_cast<const __nv_bfloat16*>(x_bf16); a.dw = dw;
+  a.rows = rows; a.c_out = c_out; a.c_in = c_in; a.ld_x = ld_x;
+  a.err = device_err_flag();
+  PN2_REQUIRE(a.err != nullptr, "wgrad_bf16: cannot allocate the device error flag");
+  const int nz = (c_in + 255) / 256, ny = (c_out + 127) / 128;
+  int nt = c_in >= 256 ? 256 : ((c_in + 15) & ~15);
+  a.nt = nt;
+  const long long chunks = (rows + 63) / 64;
+  long long ctas = 2LL * sm_count() / (ny * nz);
+  if (ctas < 1) ctas = 1;
+  if (ctas > chunks) ctas = chunks;
+  a.chunks_per_cta = (chunks + ctas - 1) / ctas;
+  ctas = (chunks + a.chunks_per_cta - 1) / a.chunks_per_cta;
+  const size_t stage = 128 * 128 + ((static_cast<size_t>(nt) * 128 + 1023) & ~static_cast<size_t>(1023));
+  const size_t smem = 2 * stage + 1024;
+  PN2_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid(static_cast<unsigned>(ctas), ny, nz);
+  wgrad_kernel<<<grid, WG_THREADS, smem, as_stream(stream)>>>(a);
+  PN2_CHECK_LAUNCH("wgrad_kernel");
+  return PN2_OK;
+}

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import mlp_train
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 
@@ -39,6 +40,15 @@ def _pool_max(x):
     return F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
 
 
+def _mlp_pool_max(mlp, grouped):
+    """``max_pool2d(mlp(grouped))`` over the nsample axis -> (B, C, npoint): pointnet2_modules.py:251-257.
+    Training mode and every call under autograd run on the tcgen05 kernels of mlp_train.py (batch-statistics
+    BatchNorm, backward, weight gradients); shapes it does not cover take torch's own layers."""
+    if mlp_train.supported(mlp, grouped):
+        return mlp_train.shared_mlp_maxpool(mlp, grouped)
+    return _pool_max(mlp(grouped))
+
+
 class _PointnetSAModuleBase(nn.Module):
     """pointnet2_modules.py:26-75: returns (new_xyz, concatenated per-scale features)."""
 
@@ -50,7 +60,7 @@ class _PointnetSAModuleBase(nn.Module):
 
     def forward(self, xyz, features=None):
         new_xyz, _ = _sample_centres(xyz, self.npoint, None)
-        outs = [_pool_max(mlp(grouper(xyz, new_xyz, features))) for grouper, mlp in zip(self.groupers, self.mlps)]
+        outs = [_mlp_pool_max(mlp, grouper(xyz, new_xyz, features)) for grouper, mlp in zip(self.groupers, self.mlps)]
         return new_xyz, torch.cat(outs, dim=1)
 
 
@@ -125,6 +135,12 @@ class PointnetSAModuleVotes(nn.Module):
             grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
         else:
             grouped_features, grouped_xyz, unique_cnt = self.grouper(xyz, new_xyz, features)
+        if self.pooling == 'max' and mlp_train.supported(self.mlp_module, grouped_features):
+            # training / autograd: shared MLP with batch-statistics BatchNorm + max-pool on the tcgen05 kernels
+            new_features = mlp_train.shared_mlp_maxpool(self.mlp_module, grouped_features)
+            if not self.ret_unique_cnt:
+                return new_xyz, new_features, inds
+            return new_xyz, new_features, inds, unique_cnt
         new_features = self.mlp_module(grouped_features)  # (B, mlp[-1], npoint, nsample)
         if self.pooling == 'max':
             new_features = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])
@@ -150,7 +166,7 @@ class PointnetSAModuleMSGVotes(nn.Module):
 
     def forward(self, xyz, features=None, inds=None):
         new_xyz, inds = _sample_centres(xyz, self.npoint, inds)
-        outs = [_pool_max(mlp(grouper(xyz, new_xyz, features))) for grouper, mlp in zip(self.groupers, self.mlps)]
+        outs = [_mlp_pool_max(mlp, grouper(xyz, new_xyz, features)) for grouper, mlp in zip(self.groupers, self.mlps)]
         return new_xyz, torch.cat(outs, dim=1), inds
 
 
@@ -182,7 +198,10 @@ class PointnetFPModule(nn.Module):
             new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)  # (B, C2 + C1, n)
         else:
             new_features = interpolated_feats
-        return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+        new_features = new_features.unsqueeze(-1)   # (B, C, n, 1): "max-pool" over one sample
+        if mlp_train.supported(self.mlp, new_features):
+            return mlp_train.shared_mlp_maxpool(self.mlp, new_features)
+        return self.mlp(new_features).squeeze(-1)
 
 
 class PointnetLFPModuleMSG(nn.Module):
@@ -198,7 +217,7 @@ class PointnetLFPModuleMSG(nn.Module):
     def forward(self, xyz2, xyz1, features2, features1):
         outs = []
         for grouper, mlp in zip(self.groupers, self.mlps):
-            f = _pool_max(mlp(grouper(xyz1, xyz2, features1)))  # (B, mlp[-1], N2)
+            f = _mlp_pool_max(mlp, grouper(xyz1, xyz2, features1))  # (B, mlp[-1], N2)
             if features2 is not None:
                 f = torch.cat([f, features2], dim=1)
             outs.append(self.post_mlp(f.unsqueeze(-1)))

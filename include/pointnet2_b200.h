@@ -253,6 +253,64 @@ int pn2_fp_prepare_indexed(int b, int n, int m, int c1, int c2, int kpad, const 
                            const float* weight, const float* unknow_feats, const float* known_feats,
                            void* out_bf16, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training-mode SharedMLP (+ max-pool): batch-statistics BatchNorm and the backward pass
+ * -- pytorch_utils.py:11-36,67-120 (Conv2d 1x1 without bias -> BatchNorm2d -> ReLU, cuDNN in the reference),
+ * pointnet2_modules.py:251-257 (max_pool2d over nsample), lib/joint/solver_3dvlp.py:580-584 (train()).
+ * Activations are point-major rows (P, C), P = B * npoint * nsample positions, row = (b*npoint + j)*nsample + s.
+ * Forward of a layer: pn2_linear_bf16 (Y fp32) -> pn2_column_stats -> pn2_bn_finalize -> pn2_bn_relu_rows
+ * (hidden) or pn2_bn_relu_maxpool (last).  Backward of a layer: pn2_bn_bwd_stats -> pn2_bn_bwd_rows ->
+ * pn2_wgrad_bf16 and pn2_linear_bf16 with the transposed weight.  All asynchronous on `stream`.
+ * ------------------------------------------------------------------------------------------- */
+
+/* sum[ch] += sum_r y[r][ch], sumsq[ch] += sum_r y[r][ch]^2 over rows of (rows, ld) fp32, ch < c <= 256.
+ * Accumulators are double and are NOT cleared by the call. */
+int pn2_column_stats(long long rows, int c, int ld, const float* y, double* sum, double* sumsq, void* stream);
+
+/* BatchNorm statistics -> per-channel affine: scale = gamma * invstd, shift = beta - mean * scale.
+ * count > 0: batch statistics from sum / sumsq over `count` positions (biased variance, torch semantics);
+ * if running_mean / running_var are non-NULL they are updated in place with `momentum` (the running
+ * variance takes the unbiased estimate).  count == 0: frozen statistics read from the running buffers.
+ * gamma / beta may be NULL (1 / 0).  mean / invstd (c) are kept for the backward pass. */
+int pn2_bn_finalize(int c, long long count, const double* sum, const double* sumsq, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                    float* scale, float* shift, float* mean, float* invstd, void* stream);
+
+/* x[r][ch] = bf16(relu(y[r][ch] * scale[ch] + shift[ch])): (rows, ld) fp32 -> (rows, c) bf16, c % 8 == 0. */
+int pn2_bn_relu_rows(long long rows, int c, int ld, const float* y, const float* scale, const float* shift,
+                     void* x_bf16, void* stream);
+
+/* Last layer: out_cm[b][ch][j] = max over the ns rows of group g = b*npoint + j of relu(y*scale + shift)
+ * (fp32, the reference's (B, C, npoint) layout) and argmax[b][ch][j] = the first slot attaining it. */
+int pn2_bn_relu_maxpool(int groups, int ns, int c, int ld, int npoint, const float* y, const float* scale,
+                        const float* shift, float* out_cm, int* argmax, void* stream);
+
+/* s1[ch] += sum dYhat, s2[ch] += sum dYhat * xhat over the rows, dYhat = upstream * [y*scale+shift > 0],
+ * xhat = (y - mean) * invstd.  Upstream: dense `da` (rows, ld_da) fp32, or (da == NULL) the pooled gradient
+ * dout_cm (B, c, npoint) routed to the arg-max slot of each group of ns rows. */
+int pn2_bn_bwd_stats(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_cm,
+                     const int* argmax, int ns, int npoint, const float* y, const float* scale,
+                     const float* shift, const float* mean, const float* invstd, double* s1, double* s2,
+                     void* stream);
+
+/* dy = bf16(gamma * invstd * (dYhat - (s1 + xhat * s2) / count))  (count > 0: batch statistics) or
+ * bf16(gamma * invstd * dYhat)  (count == 0: frozen statistics) -> (rows, c) bf16. */
+int pn2_bn_bwd_rows(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_cm,
+                    const int* argmax, int ns, int npoint, const float* y, const float* scale,
+                    const float* shift, const float* mean, const float* invstd, const float* gamma,
+                    const double* s1, const double* s2, long long count, void* dy_bf16, void* stream);
+
+/* dw[co][ci] += sum_r dy[r][co] * x[r][ci] on tcgen05 (bf16 operands, fp32 accumulation, fp32 atomics):
+ * dy (rows, c_out) bf16, x (rows, ld_x) bf16, dw (c_out, c_in) fp32 -- caller zero-fills.
+ * c_out % 8 == 0, ld_x % 8 == 0, ld_x >= c_in rounded up to 8. */
+int pn2_wgrad_bf16(long long rows, int c_out, int c_in, int ld_x, const void* dy_bf16, const void* x_bf16,
+                   float* dw, void* stream);
+
+/* rows (b*n, ld) fp32, columns [0, c) -> out[b][ch][p] at out + b*batch_stride + ch*n + p: the gradient
+ * w.r.t. a (B, C, n) tensor (or a channel slice of one) from its point-major form. */
+int pn2_unpack_rows(int b, int c, int n, int ld, long long batch_stride, const float* rows, float* out,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -385,3 +385,53 @@ def furthest_point_sampling_keyed(points, nsamples):
     tmp = torch.full((b, n), 1e10, dtype=torch.float32)
     lib().oracle_furthest_point_sampling_keyed(b, n, nsamples, _p(points), _p(tmp), _p(out))
     return out
+
+
+def shared_mlp_pool_mixed(x, weights, gammas, betas, running=None, training=True, eps=1e-5, momentum=0.1, dout=None):
+    """Numerics contract of the training-mode SharedMLP + max-pool path (3dvlp_b200/mlp_train.py) restated in
+    float64 torch with the same roundings: operands of every contraction rounded to bf16 (input, weights,
+    hidden activations, dY), everything else (BatchNorm statistics, ReLU, pooling, their gradients) unrounded.
+    x (B, C0, M, S); weights[l] (Co, Ci); running = list of (running_mean, running_var) updated in place.
+    Returns (out (B, C_last, M), grads) with grads = None or (dx, [dW], [dgamma], [dbeta]) for `dout`."""
+    X = _bf16r(x.float()).double()
+    n = len(weights)
+    saved = []
+    P = x.shape[0] * x.shape[2] * x.shape[3]
+    A = None
+    for l in range(n):
+        W = _bf16r(weights[l].float().reshape(weights[l].shape[0], -1)).double()
+        Y = torch.einsum("oc,bcms->boms", W, X).float().double()     # Y is kept in fp32 on the device
+        if training:
+            mean = Y.mean(dim=(0, 2, 3))
+            var = Y.var(dim=(0, 2, 3), unbiased=False)
+            if running is not None:
+                rm, rv = running[l]
+                rm.mul_(1 - momentum).add_(momentum * mean.float())
+                rv.mul_(1 - momentum).add_(momentum * (var * P / max(P - 1, 1)).float())
+        else:
+            mean, var = running[l][0].double(), running[l][1].double()
+        invstd = 1.0 / torch.sqrt(var + eps)
+        xhat = (Y - mean[None, :, None, None]) * invstd[None, :, None, None]
+        A = torch.relu(xhat * gammas[l].double()[None, :, None, None] + betas[l].double()[None, :, None, None])
+        saved.append((X, W, xhat, invstd, A))
+        X = _bf16r(A.float()).double()
+    out, arg = A.max(dim=3)   # first maximal slot, like F.max_pool2d
+    if dout is None:
+        return out.float(), None
+    dA = torch.zeros_like(A).scatter_(3, arg.unsqueeze(3), dout.double().unsqueeze(3))
+    dWs, dgs, dbs = [None] * n, [None] * n, [None] * n
+    for l in range(n - 1, -1, -1):
+        Xl, W, xhat, invstd, A = saved[l]
+        dYhat = dA * (A > 0)
+        s1 = dYhat.sum(dim=(0, 2, 3))
+        s2 = (dYhat * xhat).sum(dim=(0, 2, 3))
+        dgs[l], dbs[l] = s2.float(), s1.float()
+        g = (gammas[l].double() * invstd)[None, :, None, None]
+        if training:
+            dY = g * (dYhat - (s1[None, :, None, None] + xhat * s2[None, :, None, None]) / P)
+        else:
+            dY = g * dYhat
+        dY = _bf16r(dY.float()).double()
+        dWs[l] = torch.einsum("boms,bcms->oc", dY, Xl).float()
+        dA = torch.einsum("oc,boms->bcms", W, dY)
+    return out.float(), (dA.float(), dWs, dgs, dbs)

@@ -12,11 +12,15 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(autouse=True)
-def _fp32_convs():
+def _fp32_convs(pkg):
+    """These tests pin the op-by-op SEMANTICS of the module layer at fp32 accuracy (rtol 1e-4 against the
+    reference's own layers): TF32 off and the shared MLPs on torch's layers.  The tcgen05 training path has
+    its own tests with its own stated tolerance (tests/test_train_gpu.py)."""
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    yield
+    with pkg.mlp_backend("torch"):
+        yield
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 

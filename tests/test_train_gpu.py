@@ -1,0 +1,172 @@
+"""Training mode on own kernels (BASELINE config 3): SharedMLP with batch-statistics
+BatchNorm + max-pool, forward and backward, on the tcgen05 kernels of 3dvlp_b200/mlp_train.py.
+
+Checked (i) against the mixed-precision restatement of its numerics contract (oracle.shared_mlp_pool_mixed:
+bf16 operands, everything else unrounded) at a tight tolerance, (ii) against tests/golden/reference_train.npz
+-- outputs and gradients of the REFERENCE's own modules in .train() mode (fp32 torch layers) -- at the
+tolerance bf16 operands allow, (iii) against torch's own layers on the same device ("torch" backend)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from common import cloud, det_tensor, fill_state_dict  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_train.npz"))
+
+
+def _max_norm_err(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-12))
+
+
+def _mlp(pkg, widths, cuda, train=True):
+    m = pkg.pytorch_utils.SharedMLP(list(widths), bn=True)
+    fill_state_dict(m)
+    m = m.to(cuda)
+    return m.train() if train else m.eval()
+
+
+@pytest.mark.parametrize("shape,widths,train", [((2, 8, 40, 12), (8, 64, 64, 128), True),
+                                                ((3, 131, 33, 16), (131, 128, 128, 256), True),
+                                                ((2, 259, 20, 16), (259, 128, 128, 256), True),
+                                                ((2, 512, 100, 1), (512, 256, 256), True),
+                                                ((2, 4, 300, 64), (4, 64, 64, 128), True),
+                                                ((2, 8, 40, 12), (8, 64, 64, 128), False)])
+def test_shared_mlp_maxpool_vs_mixed_oracle(pkg, oracle, cuda, shape, widths, train):
+    MT = importlib.import_module("3dvlp_b200.mlp_train")
+    m = _mlp(pkg, widths, cuda, train)
+    x = (det_tensor("x%d" % shape[1], shape, 1.0) + 0.3 * det_tensor("x2", shape, 1.0).abs())
+    # repeated rows inside a group (ball-query padding): ties of the max-pool must go to the first slot
+    if shape[3] >= 4:
+        x[:, :, :, -2:] = x[:, :, :, :1]
+    dout = det_tensor("dout", (shape[0], widths[-1], shape[2]), 1.0)
+    blocks = list(m.children())
+    ws = [b.conv.weight.detach().cpu() for b in blocks]
+    gs = [b.bn.bn.weight.detach().cpu() for b in blocks]
+    bs = [b.bn.bn.bias.detach().cpu() for b in blocks]
+    running = [(b.bn.bn.running_mean.detach().cpu().clone(), b.bn.bn.running_var.detach().cpu().clone()) for b in blocks]
+    want, (dx, dWs, dgs, dbs) = oracle.shared_mlp_pool_mixed(x, ws, gs, bs, running, training=train, dout=dout)
+
+    xg = x.to(cuda).requires_grad_(True)
+    assert MT.supported(m, xg)
+    got = MT.shared_mlp_maxpool(m, xg)
+    assert got.shape == want.shape
+    scale = want.abs().max().item()
+    # contract tolerance: rtol 1e-3 with an absolute floor for the rare one-ulp bf16 flips of a hidden activation
+    torch.testing.assert_close(got.detach().cpu(), want, rtol=1e-3, atol=4e-3 * scale)
+    (got * dout.to(cuda)).sum().backward()
+    assert _max_norm_err(xg.grad, dx) < 1e-2, _max_norm_err(xg.grad, dx)
+    for l, blk in enumerate(blocks):
+        assert _max_norm_err(blk.conv.weight.grad.reshape(dWs[l].shape), dWs[l]) < 1e-2, l
+        assert _max_norm_err(blk.bn.bn.weight.grad, dgs[l]) < 1e-2, l
+        assert _max_norm_err(blk.bn.bn.bias.grad, dbs[l]) < 1e-2, l
+        if train:
+            torch.testing.assert_close(blk.bn.bn.running_mean.cpu(), running[l][0], rtol=1e-3, atol=1e-4)
+            torch.testing.assert_close(blk.bn.bn.running_var.cpu(), running[l][1], rtol=1e-3, atol=1e-4)
+            assert int(blk.bn.bn.num_batches_tracked) == 4      # fill_state_dict starts it at 3
+
+
+def test_shared_mlp_maxpool_vs_torch_layers(pkg, cuda):
+    """Same module, same input: the tcgen05 path against torch's own Conv2d / BatchNorm2d / max_pool2d (fp32)."""
+    MT = importlib.import_module("3dvlp_b200.mlp_train")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        shape, widths = (2, 131, 64, 32), (131, 128, 128, 256)
+        x = det_tensor("xt", shape, 1.0).to(cuda)
+        dout = det_tensor("dt", (2, 256, 64), 1.0).to(cuda)
+        res = {}
+        for backend in ("tcgen05", "torch"):
+            m = _mlp(pkg, widths, cuda)
+            xg = x.clone().requires_grad_(True)
+            with MT.mlp_backend(backend):
+                if MT.supported(m, xg):
+                    assert backend == "tcgen05"
+                    y = MT.shared_mlp_maxpool(m, xg)
+                else:
+                    assert backend == "torch"
+                    y = torch.nn.functional.max_pool2d(m(xg), kernel_size=[1, shape[3]]).squeeze(-1)
+            (y * dout).sum().backward()
+            res[backend] = (y.detach(), xg.grad, [p.grad for p in m.parameters()], [b.clone() for b in m.buffers()])
+        a, b = res["tcgen05"], res["torch"]
+        assert _max_norm_err(a[0], b[0]) < 2e-2
+        assert _max_norm_err(a[1], b[1]) < 4e-2
+        for ga, gb in zip(a[2], b[2]):
+            assert _max_norm_err(ga, gb) < 4e-2
+        for ba, bb in zip(a[3], b[3]):
+            assert _max_norm_err(ba.float(), bb.float()) < 2e-3
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_sa_module_train_step_vs_reference_golden(pkg, gold, cuda):
+    from make_golden_train import sa_inputs
+    xyz, feats = sa_inputs()
+    m = pkg.PointnetSAModuleVotes(npoint=40, radius=0.45, nsample=12, mlp=[5, 64, 64, 128], use_xyz=True, normalize_xyz=True)
+    fill_state_dict(m)
+    m = m.to(cuda).train()
+    x = xyz.to(cuda).requires_grad_(True)
+    f = feats.to(cuda).requires_grad_(True)
+    nx, nf, ii = m(x, f)
+    assert (ii.cpu().numpy() == gold["sa_inds"]).all()
+    np.testing.assert_array_equal(nx.detach().cpu().numpy(), gold["sa_new_xyz"])
+    assert _max_norm_err(nf.detach(), gold["sa_features"]) < 2e-2
+    ((nf * det_tensor("w_sa_f", tuple(nf.shape), 1.0).to(cuda)).sum() + (nx * det_tensor("w_sa_x", tuple(nx.shape), 1.0).to(cuda)).sum()).backward()
+    assert _max_norm_err(x.grad, gold["sa_grad_xyz"]) < 4e-2
+    assert _max_norm_err(f.grad, gold["sa_grad_features"]) < 4e-2
+    for n, p in m.named_parameters():
+        assert _max_norm_err(p.grad, gold["sa_grad_" + n]) < 4e-2, n
+    for n, b in m.named_buffers():
+        if n.endswith("num_batches_tracked"):
+            assert int(b) == int(gold["sa_buf_" + n])
+        else:
+            np.testing.assert_allclose(b.cpu().numpy(), gold["sa_buf_" + n], rtol=2e-3, atol=2e-4, err_msg=n)
+
+
+def test_fp_module_train_step_vs_reference_golden(pkg, gold, cuda):
+    from make_golden_train import fp_inputs
+    unknown, known, uf, kf = fp_inputs()
+    fp = pkg.PointnetFPModule(mlp=[20, 64, 128])
+    fill_state_dict(fp)
+    fp = fp.to(cuda).train()
+    u = uf.to(cuda).requires_grad_(True)
+    o = fp(unknown.to(cuda), known.to(cuda), u, kf.to(cuda))
+    assert _max_norm_err(o.detach(), gold["fp_out"]) < 2e-2
+    (o * det_tensor("w_fp", tuple(o.shape), 1.0).to(cuda)).sum().backward()
+    assert _max_norm_err(u.grad, gold["fp_grad_unknow_feats"]) < 4e-2
+    for n, p in fp.named_parameters():
+        assert _max_norm_err(p.grad, gold["fp_grad_" + n]) < 4e-2, n
+    for n, b in fp.named_buffers():
+        if not n.endswith("num_batches_tracked"):
+            np.testing.assert_allclose(b.cpu().numpy(), gold["fp_buf_" + n], rtol=2e-3, atol=2e-4, err_msg=n)
+
+
+def test_backbone_train_step_vs_reference_golden(pkg, gold, cuda):
+    """One training step of the whole backbone (train-mode BatchNorm in all 16 layers, backward through FP and SA
+    layers, grouping / interpolation scatter-adds) against the reference's own Pointnet2Backbone."""
+    from make_golden_train import BB_PARAMS, BB_STATS, backbone_scene
+    bb = pkg.Pointnet2Backbone(input_feature_dim=1)
+    fill_state_dict(bb)
+    bb = bb.to(cuda).train()
+    d = bb({"point_clouds": backbone_scene().to(cuda)})
+    assert (d["fp2_inds"].cpu().numpy() == gold["bb_fp2_inds"]).all()
+    assert _max_norm_err(d["sa2_features"][:, ::8, ::16].detach(), gold["bb_sa2_features_sub"]) < 3e-2
+    assert _max_norm_err(d["fp2_features"][:, ::8, ::16].detach(), gold["bb_fp2_features_sub"]) < 3e-2
+    (d["fp2_features"] * det_tensor("w_bb", tuple(d["fp2_features"].shape), 1.0).to(cuda)).sum().backward()
+    named = dict(bb.named_parameters())
+    errs = {n: _max_norm_err(named[n].grad, gold["bb_grad_" + n]) for n in BB_PARAMS}
+    assert max(errs.values()) < 8e-2, errs
+    sd = bb.state_dict()
+    for n in BB_STATS:
+        np.testing.assert_allclose(sd[n].cpu().numpy(), gold["bb_buf_" + n], rtol=5e-3, atol=5e-4, err_msg=n)
