@@ -204,6 +204,49 @@ pack_rows64_kernel(int c, int n, int kpad, const float* __restrict__ f, __nv_bfl
   }
 }
 
+// pack_rows64_kernel in the split layouts of csrc/mlp_train.cu (store_rows8): terms 2 -> (b*n, 3*kpad) rows
+// [h | l | h]; terms 3 -> (b*n, 6*kpad) rows [h | m | h | l | h | m]
+__global__ void __launch_bounds__(256)
+pack_rows64_split_kernel(int c, int n, int kpad, int terms, const float* __restrict__ f, __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[64][33];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* src = f + static_cast<size_t>(b) * c * n;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = c0 + ty + 8 * i, p = p0 + tx;
+    tile[ty + 8 * i][tx] = (ch < c && p < n) ? __ldg(src + static_cast<size_t>(ch) * n + p) : 0.f;
+  }
+  __syncthreads();
+  const int chunk = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int p = p0 + pl, ch0 = c0 + chunk * 8;
+  if (p < n && ch0 < kpad) {
+    uint32_t h[4], m[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v0 = tile[chunk * 8 + 2 * e][pl], v1 = tile[chunk * 8 + 2 * e + 1][pl];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+      const float r0 = v0 - __bfloat162float(h0), r1 = v1 - __bfloat162float(h1);
+      const __nv_bfloat16 m0 = __float2bfloat16_rn(r0), m1 = __float2bfloat16_rn(r1);
+      h[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+      m[e] = static_cast<uint32_t>(__bfloat16_as_ushort(m0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(m1)) << 16);
+      l[e] = tc::pack_bf16(r0 - __bfloat162float(m0), r1 - __bfloat162float(m1));
+    }
+    const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), mv = make_uint4(m[0], m[1], m[2], m[3]),
+                lv = make_uint4(l[0], l[1], l[2], l[3]);
+    const int blocks = terms == 2 ? 3 : 6;
+    __nv_bfloat16* row = out + (static_cast<size_t>(b) * n + p) * blocks * kpad + ch0;
+    *reinterpret_cast<uint4*>(row) = hv;
+    *reinterpret_cast<uint4*>(row + kpad) = mv;
+    *reinterpret_cast<uint4*>(row + 2 * kpad) = hv;
+    if (terms == 3) {
+      *reinterpret_cast<uint4*>(row + 3 * kpad) = lv;
+      *reinterpret_cast<uint4*>(row + 4 * kpad) = hv;
+      *reinterpret_cast<uint4*>(row + 5 * kpad) = mv;
+    }
+  }
+}
+
 // point-major rows of the input cloud, (rows, ld) fp32 with the features in columns [col0, col0+c),
 // -> (rows, kpad) bf16 zero padded: thread = 8 output channels (one 16-byte store)
 __global__ void __launch_bounds__(256)
@@ -250,6 +293,18 @@ extern "C" int pn2_pack_rows_bf16(int b, int c, int n, int kpad, const float* fe
     pack_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(c, n, kpad, features, static_cast<__nv_bfloat16*>(out));
   }
   PN2_CHECK_LAUNCH("pack_rows_kernel");
+  return PN2_OK;
+}
+
+extern "C" int pn2_pack_rows_split_bf16(int b, int c, int n, int kpad, int terms, const float* features, void* out,
+                                        void* stream) {
+  PN2_RANGE("pn2_pack_rows_split_bf16");
+  PN2_REQUIRE(b > 0 && c > 0 && n > 0 && kpad >= c && kpad % 8 == 0 && features && out && b <= 65535 &&
+                  (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (terms == 2 || terms == 3),
+              "pack_rows_split_bf16: bad arguments");
+  dim3 grid((n + 31) / 32, (kpad + 63) / 64, b);
+  pack_rows64_split_kernel<<<grid, 256, 0, as_stream(stream)>>>(c, n, kpad, terms, features, static_cast<__nv_bfloat16*>(out));
+  PN2_CHECK_LAUNCH("pack_rows64_split_kernel");
   return PN2_OK;
 }
 

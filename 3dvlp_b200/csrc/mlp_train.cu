@@ -98,10 +98,49 @@ __global__ void bn_frozen_kernel(int c, const float* __restrict__ gamma, const f
   invstd_out[ch] = invstd;
 }
 
-// X' = bf16(relu(Y * scale + shift)), thread = 8 channels of one row (one 16-byte store)
+// Operand rows of the split-precision contractions.  A value v is carried as `terms` bf16 terms
+// (h = bf16(v), m = bf16(v - h), l = bf16(v - h - m): 8, 16, 24 mantissa bits) laid out along K so that ONE
+// K-concatenated GEMM against a weight laid out in the matching order evaluates the leading products, each
+// exact in the fp32 accumulator:
+//   terms 1   [h]                      x [w_h]                                       plain bf16
+//   terms 2   [h | l | h]              x [w_h | w_h | w_l]            (here l = bf16(v - h))   ~2^-16
+//   terms 3   [h | m | h | l | h | m]  x [w_h | w_h | w_m | w_h | w_l | w_m]                   ~2^-24 (fp32 level)
+__device__ __forceinline__ void store_rows8(__nv_bfloat16* __restrict__ dst, long long r, int c, int ch0, const float (&o)[8],
+                                            int terms) {
+  uint32_t h[4], m[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(o[2 * e]), h1 = __float2bfloat16_rn(o[2 * e + 1]);
+    const float r0 = o[2 * e] - __bfloat162float(h0), r1 = o[2 * e + 1] - __bfloat162float(h1);
+    const __nv_bfloat16 m0 = __float2bfloat16_rn(r0), m1 = __float2bfloat16_rn(r1);
+    h[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+    m[e] = static_cast<uint32_t>(__bfloat16_as_ushort(m0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(m1)) << 16);
+    l[e] = tc::pack_bf16(r0 - __bfloat162float(m0), r1 - __bfloat162float(m1));
+  }
+  const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), mv = make_uint4(m[0], m[1], m[2], m[3]),
+              lv = make_uint4(l[0], l[1], l[2], l[3]);
+  if (terms <= 1) {
+    *reinterpret_cast<uint4*>(dst + r * c + ch0) = hv;
+  } else if (terms == 2) {
+    __nv_bfloat16* row = dst + r * 3 * c + ch0;
+    *reinterpret_cast<uint4*>(row) = hv;
+    *reinterpret_cast<uint4*>(row + c) = mv;
+    *reinterpret_cast<uint4*>(row + 2 * c) = hv;
+  } else {
+    __nv_bfloat16* row = dst + r * 6 * c + ch0;
+    *reinterpret_cast<uint4*>(row) = hv;
+    *reinterpret_cast<uint4*>(row + c) = mv;
+    *reinterpret_cast<uint4*>(row + 2 * c) = hv;
+    *reinterpret_cast<uint4*>(row + 3 * c) = lv;
+    *reinterpret_cast<uint4*>(row + 4 * c) = hv;
+    *reinterpret_cast<uint4*>(row + 5 * c) = mv;
+  }
+}
+
+// X' = relu(Y * scale + shift) as operand rows, thread = 8 channels of one row
 __global__ void __launch_bounds__(RT)
 bn_relu_rows_kernel(long long rows, int c, int ld, const float* __restrict__ y, const float* __restrict__ scale,
-                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ x) {
+                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ x, int terms) {
   const int chunks = c >> 3;
   const long long t = static_cast<long long>(blockIdx.x) * RT + threadIdx.x;
   if (t >= rows * chunks) return;
@@ -112,9 +151,8 @@ bn_relu_rows_kernel(long long rows, int c, int ld, const float* __restrict__ y, 
   const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
   float o[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = __fmaf_rn(v[i], __ldg(scale + ch0 + i), __ldg(shift + ch0 + i));
-  *reinterpret_cast<uint4*>(x + r * c + ch0) = make_uint4(tc::pack_bf16_relu(o[0], o[1]), tc::pack_bf16_relu(o[2], o[3]),
-                                                          tc::pack_bf16_relu(o[4], o[5]), tc::pack_bf16_relu(o[6], o[7]));
+  for (int i = 0; i < 8; ++i) o[i] = fmaxf(__fmaf_rn(v[i], __ldg(scale + ch0 + i), __ldg(shift + ch0 + i)), 0.f);
+  store_rows8(x, r, c, ch0, o, terms);
 }
 
 // out[b, ch, j] = max over the ns rows of group g = b * npoint + j of relu(y * scale + shift); arg-max = the FIRST
@@ -180,7 +218,7 @@ bn_bwd_rows_kernel(long long rows, int c, int ld_da, int ld_y, const float* __re
                    const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                    const double* __restrict__ s1, const double* __restrict__ s2, double count,
-                   __nv_bfloat16* __restrict__ dy) {
+                   __nv_bfloat16* __restrict__ dy, int terms) {
   const int chunks = c >> 3;
   const long long t = static_cast<long long>(blockIdx.x) * RT + threadIdx.x;
   if (t >= rows * chunks) return;
@@ -209,8 +247,7 @@ bn_bwd_rows_kernel(long long rows, int c, int ld_da, int ld_y, const float* __re
     const float corr = (static_cast<float>(s1[ch]) + xhat * static_cast<float>(s2[ch])) * inv_count;
     o[i] = (gamma ? __ldg(gamma + ch) : 1.f) * is * (d - corr);
   }
-  *reinterpret_cast<uint4*>(dy + r * c + ch0) = make_uint4(tc::pack_bf16(o[0], o[1]), tc::pack_bf16(o[2], o[3]),
-                                                           tc::pack_bf16(o[4], o[5]), tc::pack_bf16(o[6], o[7]));
+  store_rows8(dy, r, c, ch0, o, terms);
 }
 
 // (b * n, ld) fp32 rows, columns [0, c) -> (b, c, n) slices of a channel-major tensor with batch stride `bstride`
@@ -239,12 +276,12 @@ unpack_rows_kernel(int c, int n, int ld, long long bstride, const float* __restr
 constexpr int WG_THREADS = 128;
 
 struct WgArgs {
-  const __nv_bfloat16* dy;  // (rows, c_out)
+  const __nv_bfloat16* dy;  // (rows, ld_dy), columns [0, c_out)
   const __nv_bfloat16* x;   // (rows, ld_x)
   float* dw;                // (c_out, c_in)
   int* err;
   long long rows;
-  int c_out, c_in, ld_x, nt;  // nt = columns of this launch's N tile (multiple of 16, <= 256)
+  int c_out, c_in, ld_dy, ld_x, nt;  // nt = columns of this launch's N tile (multiple of 16, <= 256)
   long long chunks_per_cta;
 };
 
@@ -313,7 +350,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgArgs a) {
     // stage s was last read by the MMAs issued two steps ago
     if (n_issued >= 2 && !mbar_wait(&bar_mma[s], ((n_issued - 2) >> 1) & 1)) { failed = true; break; }
     const uint32_t sa = base + s * stage_bytes;
-    wg_store_tile(sa, a.dy, a.c_out, ck * 64, a.rows, co0, co_cnt, 128, tid);
+    wg_store_tile(sa, a.dy, a.ld_dy, ck * 64, a.rows, co0, co_cnt, 128, tid);
     wg_store_tile(sa + a_bytes, a.x, a.ld_x, ck * 64, a.rows, ci0, ci_cnt, a.nt, tid);
     fence_proxy_async_smem();
     tc::fence_before_sync();
@@ -404,13 +441,14 @@ extern "C" int pn2_bn_finalize(int c, long long count, const double* sum, const 
 }
 
 extern "C" int pn2_bn_relu_rows(long long rows, int c, int ld, const float* y, const float* scale, const float* shift,
-                                void* x_bf16, void* stream) {
+                                int terms, void* x_bf16, void* stream) {
   PN2_RANGE("pn2_bn_relu_rows");
   if (rows <= 0) return PN2_OK;
-  PN2_REQUIRE(c > 0 && c % 8 == 0 && ld >= c && ld % 4 == 0 && y && scale && shift && x_bf16, "bn_relu_rows: bad arguments");
+  PN2_REQUIRE(c > 0 && c % 8 == 0 && ld >= c && ld % 4 == 0 && y && scale && shift && x_bf16 && terms >= 1 && terms <= 3,
+              "bn_relu_rows: bad arguments");
   const long long total = rows * (c / 8);
   bn_relu_rows_kernel<<<static_cast<unsigned>((total + RT - 1) / RT), RT, 0, as_stream(stream)>>>(
-      rows, c, ld, y, scale, shift, static_cast<__nv_bfloat16*>(x_bf16));
+      rows, c, ld, y, scale, shift, static_cast<__nv_bfloat16*>(x_bf16), terms);
   PN2_CHECK_LAUNCH("bn_relu_rows_kernel");
   return PN2_OK;
 }
@@ -453,15 +491,17 @@ extern "C" int pn2_bn_bwd_stats(long long rows, int c, int ld_da, int ld_y, cons
 extern "C" int pn2_bn_bwd_rows(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_cm,
                                const int* argmax, int ns, int npoint, const float* y, const float* scale,
                                const float* shift, const float* mean, const float* invstd, const float* gamma,
-                               const double* s1, const double* s2, long long count, void* dy_bf16, void* stream) {
+                               const double* s1, const double* s2, long long count, int terms, void* dy_bf16,
+                               void* stream) {
   PN2_RANGE("pn2_bn_bwd_rows");
   if (rows <= 0) return PN2_OK;
-  PN2_REQUIRE(c > 0 && c % 8 == 0 && y && scale && shift && mean && invstd && s1 && s2 && dy_bf16, "bn_bwd_rows: bad arguments");
+  PN2_REQUIRE(c > 0 && c % 8 == 0 && y && scale && shift && mean && invstd && s1 && s2 && dy_bf16 && terms >= 1 && terms <= 3,
+              "bn_bwd_rows: bad arguments");
   PN2_REQUIRE(da || (dout_cm && argmax && ns > 0 && npoint > 0), "bn_bwd_rows: no upstream gradient");
   const long long total = rows * (c / 8);
   bn_bwd_rows_kernel<<<static_cast<unsigned>((total + RT - 1) / RT), RT, 0, as_stream(stream)>>>(
       rows, c, ld_da, ld_y, da, dout_cm, argmax, ns, npoint, y, scale, shift, mean, invstd, gamma, s1, s2,
-      static_cast<double>(count), static_cast<__nv_bfloat16*>(dy_bf16));
+      static_cast<double>(count), static_cast<__nv_bfloat16*>(dy_bf16), terms);
   PN2_CHECK_LAUNCH("bn_bwd_rows_kernel");
   return PN2_OK;
 }
@@ -477,15 +517,18 @@ extern "C" int pn2_unpack_rows(int b, int c, int n, int ld, long long batch_stri
   return PN2_OK;
 }
 
-extern "C" int pn2_wgrad_bf16(long long rows, int c_out, int c_in, int ld_x, const void* dy_bf16, const void* x_bf16,
-                              float* dw, void* stream) {
+extern "C" int pn2_wgrad_bf16(long long rows, int c_out, int c_in, int ld_dy, int ld_x, const void* dy_bf16,
+                              const void* x_bf16, float* dw, void* stream) {
   PN2_RANGE("pn2_wgrad_bf16");
   if (rows <= 0) return PN2_OK;
-  PN2_REQUIRE(c_out > 0 && c_out % 8 == 0 && c_in > 0 && ld_x % 8 == 0 && ld_x >= ((c_in + 7) & ~7) && dy_bf16 && x_bf16 && dw,
-              "wgrad_bf16: bad arguments (c_out %% 8, ld_x %% 8, ld_x >= c_in rounded up to 8)");
+  PN2_REQUIRE(c_out > 0 && c_out % 8 == 0 && c_in > 0 && ld_x % 8 == 0 && ld_x >= ((c_in + 7) & ~7) && ld_dy % 8 == 0 &&
+                  ld_dy >= c_out && dy_bf16 && x_bf16 && dw,
+              "wgrad_bf16: bad arguments (c_out %% 8, ld_dy / ld_x %% 8, ld_x >= c_in rounded up to 8)");
+  PN2_REQUIRE(((reinterpret_cast<uintptr_t>(dy_bf16) | reinterpret_cast<uintptr_t>(x_bf16)) & 15) == 0,
+              "wgrad_bf16: operands must be 16-byte aligned");
   WgArgs a;
   a.dy = static_cast<const __nv_bfloat16*>(dy_bf16); a.x = static_cast<const __nv_bfloat16*>(x_bf16); a.dw = dw;
-  a.rows = rows; a.c_out = c_out; a.c_in = c_in; a.ld_x = ld_x;
+  a.rows = rows; a.c_out = c_out; a.c_in = c_in; a.ld_dy = ld_dy; a.ld_x = ld_x;
   a.err = device_err_flag();
   PN2_REQUIRE(a.err != nullptr, "wgrad_bf16: cannot allocate the device error flag");
   const int nz = (c_in + 255) / 256, ny = (c_out + 127) / 128;

@@ -8,11 +8,23 @@ by ``F.max_pool2d`` over the nsample axis (pointnet2_modules.py:251-257), on the
 operands and fp32 accumulation; BatchNorm statistics are accumulated in double; everything else is fused
 elementwise / reduction kernels (csrc/mlp_train.cu, C ABI in include/pointnet2_b200.h).
 
-Numerics contract (restated by oracle.shared_mlp_pool_train_mixed): X0 = bf16(input); per layer
-Y = X W^T with bf16(W), fp32 accumulate, Y kept in fp32; mean / biased variance of Y over all positions;
-A = relu(Y * scale + shift) in fp32; hidden A rounded to bf16 as the next operand; output = max over nsample
-of the last A (fp32).  Backward: BatchNorm / ReLU / max-pool gradients in fp32, dY rounded to bf16 as the
-operand of dW = dY^T X and dX = dY W.
+Numerics contract (restated by oracle.shared_mlp_pool_mixed).  Every operand of a contraction (input,
+weights, hidden activations, dY) is carried as up to three bf16 terms, v = h + m + l with h = bf16(v),
+m = bf16(v - h), l = bf16(v - h - m), and a product a.b is evaluated on the tensor cores as the sum of its
+leading term products, each exact in the fp32 accumulator:
+  "bf16x6" (default)  3 terms, 6 products (hh, mh, hm, lh, hl, mm): ~2^-24 relative, i.e. fp32-level -- the
+                      reference trains in fp32, and a stack of batch-normalised layers amplifies operand
+                      rounding by |mean|/std per layer (measured on the backbone: 8e-5 at SA1 -> 0.2 at FP2
+                      with 16-bit operands);
+  "bf16x3"            2 terms, 3 products: ~2^-16 relative (60x tighter than the TF32 convolutions torch runs
+                      the reference with by default), half the operand traffic of bf16x6;
+  "bf16"              1 term: the eval path's contract.  Fast, but the gradient of a max-pool is discontinuous:
+                      with 2^-9 operand rounding the arg-max of a few per cent of the (channel, centre) entries
+                      differs from the fp32 reference's and moves their whole gradient to another neighbour --
+                      15-35 % rms gradient error measured on random inputs although every kernel is exact
+                      w.r.t. its contract.  Per layer: Y = X W^T kept in fp32; mean / biased variance of Y over all positions
+(double accumulators); A = relu(Y * scale + shift) in fp32; output = max over nsample of the last A (fp32).
+Backward: BatchNorm / ReLU / max-pool gradients in fp32, dW = dY^T X and dX = dY W as above.
 """
 import ctypes
 
@@ -24,6 +36,29 @@ from . import _lib as L
 from . import tensorcore as tcm
 
 _BACKEND = ["tcgen05"]   # or "torch": the reference's cuDNN layers (fp32), kept for semantic cross-checks
+_PRECISION = ["bf16x6"]  # or "bf16x3", "bf16"
+_TERMS = {"bf16": 1, "bf16x3": 2, "bf16x6": 3}
+# K-block order of the operand rows / of the weights per number of terms (0 = h, 1 = m, 2 = l): block i of the
+# rows meets block i of the weight; (row term, weight term) pairs = the leading products
+_ROW_BLOCKS = {1: (0,), 2: (0, 1, 0), 3: (0, 1, 0, 2, 0, 1)}
+_W_BLOCKS = {1: (0,), 2: (0, 0, 1), 3: (0, 0, 1, 0, 2, 1)}
+
+
+class precision:
+    """``with precision("bf16"): ...`` -- operand precision of the training contractions (module docstring)."""
+
+    def __init__(self, name):
+        assert name in _TERMS
+        self.name = name
+
+    def __enter__(self):
+        self.prev = _PRECISION[0]
+        _PRECISION[0] = self.name
+        return self
+
+    def __exit__(self, *exc):
+        _PRECISION[0] = self.prev
+        return False
 
 
 class mlp_backend:
@@ -68,6 +103,29 @@ def _f(v):
     return ctypes.c_float(v)
 
 
+def _pack_weight(w2d, kpad, terms):
+    """(n, k) fp32 -> PackedWeight over the K blocks of `terms` (each of width kpad, zero padded)."""
+    n, k = w2d.shape
+    wp = w2d.new_zeros(n, kpad)
+    wp[:, :k] = w2d
+    if terms > 1:
+        h = wp.to(torch.bfloat16).float()
+        m = (wp - h).to(torch.bfloat16).float()
+        parts = (h, m, wp - h - m)
+        wp = torch.cat([parts[t] for t in _W_BLOCKS[terms]], dim=1)
+    return tcm.PackedWeight(wp)
+
+
+def _pack_input(x3, kpad, terms):
+    """(B, C, n) fp32 channel-major -> operand rows (B*n, blocks * kpad) in the layout of `terms`."""
+    if terms == 1:
+        return tcm.pack_rows(x3, kpad)
+    b, c, n = x3.shape
+    out = torch.empty(b * n, len(_ROW_BLOCKS[terms]) * kpad, device=x3.device, dtype=torch.bfloat16)
+    L.call("pn2_pack_rows_split_bf16", b, c, n, kpad, terms, L.ptr(x3), L.ptr(out), L.stream_of(x3), device=x3.device)
+    return out
+
+
 def _ll(v):
     return ctypes.c_longlong(v)
 
@@ -83,12 +141,14 @@ class _SharedMLPMaxPool(Function):
         n_layers = len(bns)
         st = L.stream_of(x)
         xs, ys, affine = [], [], []
-        X = tcm.pack_rows(x.reshape(B, C0, M * S).contiguous(), tcm.kpad64(C0))      # (P, kpad) bf16
+        split = _TERMS[_PRECISION[0]]       # number of bf16 terms per operand
+        kw = tcm.kpad64(C0)                                                           # width of one operand block
+        X = _pack_input(x.reshape(B, C0, M * S).contiguous(), kw, split)              # (P, kw) or (P, 3 kw) bf16
         out = arg = None
         for i, bn in enumerate(bns):
             w, gamma, beta = params[3 * i], params[3 * i + 1], params[3 * i + 2]
             co = w.shape[0]
-            wp = tcm.PackedWeight(w.detach().reshape(co, -1))
+            wp = _pack_weight(w.detach().reshape(co, -1).float(), kw, split)
             Y = tcm.linear(X, wp, None, relu=False, out="f32")                        # (P, co) fp32
             aff = torch.empty(4, co, device=dev, dtype=torch.float32)                 # scale, shift, mean, invstd
             if training:
@@ -106,20 +166,22 @@ class _SharedMLPMaxPool(Function):
                        L.ptr(aff[3]), st, device=dev)
             xs.append(X); ys.append(Y); affine.append(aff)
             if i + 1 < n_layers:
-                X = torch.empty(P, co, device=dev, dtype=torch.bfloat16)
-                L.call("pn2_bn_relu_rows", _ll(P), co, co, L.ptr(Y), L.ptr(aff[0]), L.ptr(aff[1]), L.ptr(X), st, device=dev)
+                X = torch.empty(P, len(_ROW_BLOCKS[split]) * co, device=dev, dtype=torch.bfloat16)
+                L.call("pn2_bn_relu_rows", _ll(P), co, co, L.ptr(Y), L.ptr(aff[0]), L.ptr(aff[1]), split, L.ptr(X), st,
+                       device=dev)
+                kw = co
             else:
                 out = torch.empty(B, co, M, device=dev, dtype=torch.float32)
                 arg = torch.empty(B, co, M, device=dev, dtype=torch.int32)
                 L.call("pn2_bn_relu_maxpool", B * M, S, co, co, M, L.ptr(Y), L.ptr(aff[0]), L.ptr(aff[1]), L.ptr(out),
                        L.ptr(arg), st, device=dev)
         ctx.save_for_backward(arg, *xs, *ys, *affine, *params)
-        ctx.meta = (B, C0, M, S, n_layers, bool(training))
+        ctx.meta = (B, C0, M, S, n_layers, bool(training), split)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        B, C0, M, S, n, training = ctx.meta
+        B, C0, M, S, n, training, split = ctx.meta
         saved = ctx.saved_tensors
         arg = saved[0]
         xs, ys, affine, params = saved[1:1 + n], saved[1 + n:1 + 2 * n], saved[1 + 2 * n:1 + 3 * n], saved[1 + 3 * n:]
@@ -141,12 +203,21 @@ class _SharedMLPMaxPool(Function):
                    L.ptr(aff[3]), L.ptr(s[0]), L.ptr(s[1]), st, device=dev)
             grads[3 * i + 1] = s[1].float()   # d gamma = sum dYhat * xhat
             grads[3 * i + 2] = s[0].float()   # d beta  = sum dYhat
-            dY = torch.empty(P, co, device=dev, dtype=torch.bfloat16)
+            blocks = len(_ROW_BLOCKS[split])
+            dY = torch.empty(P, blocks * co, device=dev, dtype=torch.bfloat16)
             L.call("pn2_bn_bwd_rows", _ll(P), co, ld_da, co, L.ptr(da), L.ptr(dout if da is None else None),
                    L.ptr(arg if da is None else None), S, M, L.ptr(Y), L.ptr(aff[0]), L.ptr(aff[1]), L.ptr(aff[2]),
-                   L.ptr(aff[3]), L.ptr(gamma), L.ptr(s[0]), L.ptr(s[1]), _ll(P if training else 0), L.ptr(dY), st, device=dev)
+                   L.ptr(aff[3]), L.ptr(gamma), L.ptr(s[0]), L.ptr(s[1]), _ll(P if training else 0), split, L.ptr(dY), st,
+                   device=dev)
             dW = torch.zeros(co, ci, device=dev, dtype=torch.float32)
-            L.call("pn2_wgrad_bf16", _ll(P), co, ci, X.shape[1], L.ptr(dY), L.ptr(X), L.ptr(dW), st, device=dev)
+            kx = X.shape[1] // blocks                        # width of one operand block of X
+            # dW = dY^T X: one launch per leading (dY term, X term) product, on the column blocks holding the terms
+            first = {t: _ROW_BLOCKS[split].index(t) for t in set(_ROW_BLOCKS[split])}   # term -> first block
+            for dy_t, x_t in set(zip(_ROW_BLOCKS[split], _W_BLOCKS[split])):
+                dy_blk, x_blk = first[dy_t], first[x_t]
+                L.call("pn2_wgrad_bf16", _ll(P), co, ci, blocks * co, blocks * kx,
+                       ctypes.c_void_p(dY.data_ptr() + 2 * dy_blk * co), ctypes.c_void_p(X.data_ptr() + 2 * x_blk * kx),
+                       L.ptr(dW), st, device=dev)
             grads[3 * i] = dW.view_as(w)
             if i == 0 and not ctx.needs_input_grad[0]:
                 break
@@ -159,7 +230,7 @@ class _SharedMLPMaxPool(Function):
                 rows_pad = (c1 - c0 + 15) // 16 * 16
                 blk = torch.zeros(rows_pad, co, device=dev, dtype=torch.float32)
                 blk[:c1 - c0] = wt[c0:c1]
-                pieces.append((c0, c1, rows_pad, tcm.linear(dY, tcm.PackedWeight(blk), None, relu=False, out="f32")))
+                pieces.append((c0, c1, rows_pad, tcm.linear(dY, _pack_weight(blk, co, split), None, relu=False, out="f32")))
             if i > 0:
                 assert len(pieces) == 1   # hidden widths are <= 256
                 da, ld_da = pieces[0][3], pieces[0][2]

@@ -276,9 +276,20 @@ int pn2_bn_finalize(int c, long long count, const double* sum, const double* sum
                     const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                     float* scale, float* shift, float* mean, float* invstd, void* stream);
 
-/* x[r][ch] = bf16(relu(y[r][ch] * scale[ch] + shift[ch])): (rows, ld) fp32 -> (rows, c) bf16, c % 8 == 0. */
+/* Operand rows x = relu(y * scale + shift) of the next contraction: (rows, ld) fp32 -> bf16, c % 8 == 0.
+ * A value is carried as `terms` bf16 terms (h = bf16(x), m = bf16(x - h), l = bf16(x - h - m)) laid out along K
+ * so that ONE K-concatenated pn2_linear_bf16 against a weight laid out in the matching order evaluates the
+ * leading products, each exact in the fp32 accumulator:
+ *   terms 1: (rows, c)   [h]                      x [w_h]                                   plain bf16
+ *   terms 2: (rows, 3c)  [h | m | h]              x [w_h | w_h | w_m]                       ~2^-16 relative
+ *   terms 3: (rows, 6c)  [h | m | h | l | h | m]  x [w_h | w_h | w_m | w_h | w_l | w_m]     ~2^-24 (fp32 level) */
 int pn2_bn_relu_rows(long long rows, int c, int ld, const float* y, const float* scale, const float* shift,
-                     void* x_bf16, void* stream);
+                     int terms, void* x_bf16, void* stream);
+
+/* pn2_pack_rows_bf16 in the split layouts above (terms 2 or 3, blocks of width kpad): features (b,c,n) fp32 ->
+ * (b*n, 3*kpad) or (b*n, 6*kpad) bf16 rows. */
+int pn2_pack_rows_split_bf16(int b, int c, int n, int kpad, int terms, const float* features, void* out,
+                             void* stream);
 
 /* Last layer: out_cm[b][ch][j] = max over the ns rows of group g = b*npoint + j of relu(y*scale + shift)
  * (fp32, the reference's (B, C, npoint) layout) and argmax[b][ch][j] = the first slot attaining it. */
@@ -293,18 +304,21 @@ int pn2_bn_bwd_stats(long long rows, int c, int ld_da, int ld_y, const float* da
                      const float* shift, const float* mean, const float* invstd, double* s1, double* s2,
                      void* stream);
 
-/* dy = bf16(gamma * invstd * (dYhat - (s1 + xhat * s2) / count))  (count > 0: batch statistics) or
- * bf16(gamma * invstd * dYhat)  (count == 0: frozen statistics) -> (rows, c) bf16. */
+/* dy = gamma * invstd * (dYhat - (s1 + xhat * s2) / count)  (count > 0: batch statistics) or
+ * gamma * invstd * dYhat  (count == 0: frozen statistics) -> operand rows in the `terms` layout of
+ * pn2_bn_relu_rows: (rows, c), (rows, 3c) or (rows, 6c) bf16. */
 int pn2_bn_bwd_rows(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_cm,
                     const int* argmax, int ns, int npoint, const float* y, const float* scale,
                     const float* shift, const float* mean, const float* invstd, const float* gamma,
-                    const double* s1, const double* s2, long long count, void* dy_bf16, void* stream);
+                    const double* s1, const double* s2, long long count, int terms, void* dy_bf16,
+                    void* stream);
 
 /* dw[co][ci] += sum_r dy[r][co] * x[r][ci] on tcgen05 (bf16 operands, fp32 accumulation, fp32 atomics):
- * dy (rows, c_out) bf16, x (rows, ld_x) bf16, dw (c_out, c_in) fp32 -- caller zero-fills.
- * c_out % 8 == 0, ld_x % 8 == 0, ld_x >= c_in rounded up to 8. */
-int pn2_wgrad_bf16(long long rows, int c_out, int c_in, int ld_x, const void* dy_bf16, const void* x_bf16,
-                   float* dw, void* stream);
+ * dy (rows, ld_dy) bf16 columns [0, c_out), x (rows, ld_x) bf16 columns [0, c_in), dw (c_out, c_in) fp32 --
+ * caller zero-fills.  c_out % 8 == 0, ld_dy % 8 == 0, ld_x % 8 == 0, ld_x >= c_in rounded up to 8; pointers
+ * 16-byte aligned.  Split-precision gradients are three calls on the h / l column blocks of the operands. */
+int pn2_wgrad_bf16(long long rows, int c_out, int c_in, int ld_dy, int ld_x, const void* dy_bf16,
+                   const void* x_bf16, float* dw, void* stream);
 
 /* rows (b*n, ld) fp32, columns [0, c) -> out[b][ch][p] at out + b*batch_stride + ch*n + p: the gradient
  * w.r.t. a (B, C, n) tensor (or a channel slice of one) from its point-major form. */

@@ -387,20 +387,42 @@ def furthest_point_sampling_keyed(points, nsamples):
     return out
 
 
-def shared_mlp_pool_mixed(x, weights, gammas, betas, running=None, training=True, eps=1e-5, momentum=0.1, dout=None):
+def _terms(t, n):
+    """v -> its first n bf16 terms (h = bf16(v), m = bf16(v - h), l = bf16(v - h - m)) as float64 tensors."""
+    out, rest = [], t.float()
+    for _ in range(n):
+        h = _bf16r(rest)
+        out.append(h.double())
+        rest = rest - h
+    return out
+
+
+_PRODUCTS = {1: ((0, 0),), 2: ((0, 0), (1, 0), (0, 1)), 3: ((0, 0), (1, 0), (0, 1), (2, 0), (0, 2), (1, 1))}
+
+
+def _contract(eq, a, b, terms):
+    """einsum(eq, a, b) under the operand contract of 3dvlp_b200/mlp_train.py: both operands as `terms` bf16
+    terms, the leading term products summed exactly."""
+    at, bt = _terms(a, terms), _terms(b, terms)
+    return sum(torch.einsum(eq, at[i], bt[j]) for i, j in _PRODUCTS[terms])
+
+
+def shared_mlp_pool_mixed(x, weights, gammas, betas, running=None, training=True, eps=1e-5, momentum=0.1, dout=None,
+                          terms=3):
     """Numerics contract of the training-mode SharedMLP + max-pool path (3dvlp_b200/mlp_train.py) restated in
-    float64 torch with the same roundings: operands of every contraction rounded to bf16 (input, weights,
-    hidden activations, dY), everything else (BatchNorm statistics, ReLU, pooling, their gradients) unrounded.
+    float64 torch with the same operand roundings: every operand of a contraction (input, weights, hidden
+    activations, dY) as `terms` bf16 terms with the leading products (3: "bf16x6", 2: "bf16x3", 1: "bf16");
+    everything else (BatchNorm statistics, ReLU, pooling, their gradients) unrounded.
     x (B, C0, M, S); weights[l] (Co, Ci); running = list of (running_mean, running_var) updated in place.
     Returns (out (B, C_last, M), grads) with grads = None or (dx, [dW], [dgamma], [dbeta]) for `dout`."""
-    X = _bf16r(x.float()).double()
+    X = x.double()
     n = len(weights)
     saved = []
     P = x.shape[0] * x.shape[2] * x.shape[3]
     A = None
     for l in range(n):
-        W = _bf16r(weights[l].float().reshape(weights[l].shape[0], -1)).double()
-        Y = torch.einsum("oc,bcms->boms", W, X).float().double()     # Y is kept in fp32 on the device
+        W = weights[l].double().reshape(weights[l].shape[0], -1)
+        Y = _contract("oc,bcms->boms", W, X, terms).float().double()     # Y is kept in fp32 on the device
         if training:
             mean = Y.mean(dim=(0, 2, 3))
             var = Y.var(dim=(0, 2, 3), unbiased=False)
@@ -414,7 +436,7 @@ def shared_mlp_pool_mixed(x, weights, gammas, betas, running=None, training=True
         xhat = (Y - mean[None, :, None, None]) * invstd[None, :, None, None]
         A = torch.relu(xhat * gammas[l].double()[None, :, None, None] + betas[l].double()[None, :, None, None])
         saved.append((X, W, xhat, invstd, A))
-        X = _bf16r(A.float()).double()
+        X = A.float().double()
     out, arg = A.max(dim=3)   # first maximal slot, like F.max_pool2d
     if dout is None:
         return out.float(), None
@@ -431,7 +453,7 @@ def shared_mlp_pool_mixed(x, weights, gammas, betas, running=None, training=True
             dY = g * (dYhat - (s1[None, :, None, None] + xhat * s2[None, :, None, None]) / P)
         else:
             dY = g * dYhat
-        dY = _bf16r(dY.float()).double()
-        dWs[l] = torch.einsum("boms,bcms->oc", dY, Xl).float()
-        dA = torch.einsum("oc,boms->bcms", W, dY)
+        dY = dY.float().double()
+        dWs[l] = _contract("boms,bcms->oc", dY, Xl, terms).float()
+        dA = _contract("oc,boms->bcms", W, dY, terms)
     return out.float(), (dA.float(), dWs, dgs, dbs)

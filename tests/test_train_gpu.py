@@ -1,10 +1,11 @@
 """Training mode on own kernels (BASELINE config 3): SharedMLP with batch-statistics
 BatchNorm + max-pool, forward and backward, on the tcgen05 kernels of 3dvlp_b200/mlp_train.py.
 
-Checked (i) against the mixed-precision restatement of its numerics contract (oracle.shared_mlp_pool_mixed:
-bf16 operands, everything else unrounded) at a tight tolerance, (ii) against tests/golden/reference_train.npz
--- outputs and gradients of the REFERENCE's own modules in .train() mode (fp32 torch layers) -- at the
-tolerance bf16 operands allow, (iii) against torch's own layers on the same device ("torch" backend)."""
+Checked (i) against the restatement of its numerics contract (oracle.shared_mlp_pool_mixed: split-bf16
+operands, everything else unrounded), (ii) against tests/golden/reference_train.npz -- outputs and gradients of
+the REFERENCE's own modules in .train() mode (fp32 torch layers): forward at rtol 1e-3, running statistics at
+1e-4, gradients at 2 % relative rms (a max-pool gradient is discontinuous: see _rms_err), (iii) against torch's
+own layers on the same device ("torch" backend)."""
 import importlib
 import os
 import sys
@@ -30,6 +31,21 @@ def _max_norm_err(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-12))
 
 
+def _rms_err(a, b):
+    """Relative root-mean-square error: the measure for gradients.  A max-pool gradient is discontinuous in its
+    input -- where two neighbours of a ball are within bf16 round-off of each other the arg-max may legitimately
+    differ between two correctly rounded evaluations and one (channel, centre) entry of the gradient moves to
+    another slot -- so isolated elements can differ by O(1) while every systematic error shows up here."""
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp(min=1e-12))
+
+
+def _rand(name, shape, scale=1.0):
+    import zlib
+    rs = np.random.RandomState(zlib.crc32(name.encode()) % (2 ** 31))
+    return torch.from_numpy((rs.normal(size=shape) * scale).astype(np.float32))
+
+
 def _mlp(pkg, widths, cuda, train=True):
     m = pkg.pytorch_utils.SharedMLP(list(widths), bn=True)
     fill_state_dict(m)
@@ -37,40 +53,48 @@ def _mlp(pkg, widths, cuda, train=True):
     return m.train() if train else m.eval()
 
 
+@pytest.mark.parametrize("prec", ["bf16x6", "bf16x3", "bf16"])
 @pytest.mark.parametrize("shape,widths,train", [((2, 8, 40, 12), (8, 64, 64, 128), True),
                                                 ((3, 131, 33, 16), (131, 128, 128, 256), True),
                                                 ((2, 259, 20, 16), (259, 128, 128, 256), True),
                                                 ((2, 512, 100, 1), (512, 256, 256), True),
                                                 ((2, 4, 300, 64), (4, 64, 64, 128), True),
                                                 ((2, 8, 40, 12), (8, 64, 64, 128), False)])
-def test_shared_mlp_maxpool_vs_mixed_oracle(pkg, oracle, cuda, shape, widths, train):
+def test_shared_mlp_maxpool_vs_mixed_oracle(pkg, oracle, cuda, shape, widths, train, prec):
     MT = importlib.import_module("3dvlp_b200.mlp_train")
+    terms = {"bf16": 1, "bf16x3": 2, "bf16x6": 3}[prec]
+    split = terms > 1
     m = _mlp(pkg, widths, cuda, train)
-    x = (det_tensor("x%d" % shape[1], shape, 1.0) + 0.3 * det_tensor("x2", shape, 1.0).abs())
-    # repeated rows inside a group (ball-query padding): ties of the max-pool must go to the first slot
+    x = _rand("x%d" % shape[1], shape)
+    # repeated rows inside a group (ball-query padding): exact ties of the max-pool must go to the first slot
     if shape[3] >= 4:
         x[:, :, :, -2:] = x[:, :, :, :1]
-    dout = det_tensor("dout", (shape[0], widths[-1], shape[2]), 1.0)
+    dout = _rand("dout", (shape[0], widths[-1], shape[2]))
     blocks = list(m.children())
     ws = [b.conv.weight.detach().cpu() for b in blocks]
     gs = [b.bn.bn.weight.detach().cpu() for b in blocks]
     bs = [b.bn.bn.bias.detach().cpu() for b in blocks]
     running = [(b.bn.bn.running_mean.detach().cpu().clone(), b.bn.bn.running_var.detach().cpu().clone()) for b in blocks]
-    want, (dx, dWs, dgs, dbs) = oracle.shared_mlp_pool_mixed(x, ws, gs, bs, running, training=train, dout=dout)
+    want, (dx, dWs, dgs, dbs) = oracle.shared_mlp_pool_mixed(x, ws, gs, bs, running, training=train, dout=dout, terms=terms)
 
     xg = x.to(cuda).requires_grad_(True)
     assert MT.supported(m, xg)
-    got = MT.shared_mlp_maxpool(m, xg)
+    with MT.precision(prec):
+        got = MT.shared_mlp_maxpool(m, xg)
     assert got.shape == want.shape
     scale = want.abs().max().item()
-    # contract tolerance: rtol 1e-3 with an absolute floor for the rare one-ulp bf16 flips of a hidden activation
-    torch.testing.assert_close(got.detach().cpu(), want, rtol=1e-3, atol=4e-3 * scale)
+    # contract tolerance: rtol 1e-3; plain bf16 operands get an absolute floor for the rare one-ulp flips of a
+    # hidden activation (2^-9 of one of K terms), the split operands (2^-17) do not need one
+    torch.testing.assert_close(got.detach().cpu(), want, rtol=1e-3, atol=(1e-4 if split else 4e-3) * scale)
     (got * dout.to(cuda)).sum().backward()
-    assert _max_norm_err(xg.grad, dx) < 1e-2, _max_norm_err(xg.grad, dx)
+    tol = 1e-2 if split else 6e-2   # relative rms; arg-max flips between two evaluations of the same contract
+    assert _rms_err(xg.grad, dx) < tol, _rms_err(xg.grad, dx)
+    if shape[3] >= 4:  # the gradient of a tied group goes to its FIRST slot, none to the repeated rows' pooled share
+        assert float(xg.grad[:, :, :, 0].abs().sum()) > float(xg.grad[:, :, :, -1].abs().sum())
     for l, blk in enumerate(blocks):
-        assert _max_norm_err(blk.conv.weight.grad.reshape(dWs[l].shape), dWs[l]) < 1e-2, l
-        assert _max_norm_err(blk.bn.bn.weight.grad, dgs[l]) < 1e-2, l
-        assert _max_norm_err(blk.bn.bn.bias.grad, dbs[l]) < 1e-2, l
+        assert _rms_err(blk.conv.weight.grad.reshape(dWs[l].shape), dWs[l]) < tol, l
+        assert _rms_err(blk.bn.bn.weight.grad, dgs[l]) < tol, l
+        assert _rms_err(blk.bn.bn.bias.grad, dbs[l]) < tol, l
         if train:
             torch.testing.assert_close(blk.bn.bn.running_mean.cpu(), running[l][0], rtol=1e-3, atol=1e-4)
             torch.testing.assert_close(blk.bn.bn.running_var.cpu(), running[l][1], rtol=1e-3, atol=1e-4)
@@ -84,8 +108,8 @@ def test_shared_mlp_maxpool_vs_torch_layers(pkg, cuda):
     torch.backends.cudnn.allow_tf32 = False
     try:
         shape, widths = (2, 131, 64, 32), (131, 128, 128, 256)
-        x = det_tensor("xt", shape, 1.0).to(cuda)
-        dout = det_tensor("dt", (2, 256, 64), 1.0).to(cuda)
+        x = _rand("xt", shape).to(cuda)
+        dout = _rand("dt", (2, 256, 64)).to(cuda)
         res = {}
         for backend in ("tcgen05", "torch"):
             m = _mlp(pkg, widths, cuda)
@@ -100,12 +124,12 @@ def test_shared_mlp_maxpool_vs_torch_layers(pkg, cuda):
             (y * dout).sum().backward()
             res[backend] = (y.detach(), xg.grad, [p.grad for p in m.parameters()], [b.clone() for b in m.buffers()])
         a, b = res["tcgen05"], res["torch"]
-        assert _max_norm_err(a[0], b[0]) < 2e-2
-        assert _max_norm_err(a[1], b[1]) < 4e-2
+        assert _max_norm_err(a[0], b[0]) < 1e-3
+        assert _rms_err(a[1], b[1]) < 2e-2
         for ga, gb in zip(a[2], b[2]):
-            assert _max_norm_err(ga, gb) < 4e-2
+            assert _rms_err(ga, gb) < 2e-2
         for ba, bb in zip(a[3], b[3]):
-            assert _max_norm_err(ba.float(), bb.float()) < 2e-3
+            assert _max_norm_err(ba.float(), bb.float()) < 1e-4
     finally:
         torch.backends.cudnn.allow_tf32 = old
 
@@ -121,17 +145,17 @@ def test_sa_module_train_step_vs_reference_golden(pkg, gold, cuda):
     nx, nf, ii = m(x, f)
     assert (ii.cpu().numpy() == gold["sa_inds"]).all()
     np.testing.assert_array_equal(nx.detach().cpu().numpy(), gold["sa_new_xyz"])
-    assert _max_norm_err(nf.detach(), gold["sa_features"]) < 2e-2
+    np.testing.assert_allclose(nf.detach().cpu().numpy(), gold["sa_features"], rtol=1e-3, atol=1e-4 * float(np.abs(gold["sa_features"]).max()))
     ((nf * det_tensor("w_sa_f", tuple(nf.shape), 1.0).to(cuda)).sum() + (nx * det_tensor("w_sa_x", tuple(nx.shape), 1.0).to(cuda)).sum()).backward()
-    assert _max_norm_err(x.grad, gold["sa_grad_xyz"]) < 4e-2
-    assert _max_norm_err(f.grad, gold["sa_grad_features"]) < 4e-2
+    assert _rms_err(x.grad, gold["sa_grad_xyz"]) < 2e-2
+    assert _rms_err(f.grad, gold["sa_grad_features"]) < 2e-2
     for n, p in m.named_parameters():
-        assert _max_norm_err(p.grad, gold["sa_grad_" + n]) < 4e-2, n
+        assert _rms_err(p.grad, gold["sa_grad_" + n]) < 2e-2, n
     for n, b in m.named_buffers():
         if n.endswith("num_batches_tracked"):
             assert int(b) == int(gold["sa_buf_" + n])
         else:
-            np.testing.assert_allclose(b.cpu().numpy(), gold["sa_buf_" + n], rtol=2e-3, atol=2e-4, err_msg=n)
+            np.testing.assert_allclose(b.cpu().numpy(), gold["sa_buf_" + n], rtol=1e-4, atol=1e-5, err_msg=n)
 
 
 def test_fp_module_train_step_vs_reference_golden(pkg, gold, cuda):
@@ -142,31 +166,52 @@ def test_fp_module_train_step_vs_reference_golden(pkg, gold, cuda):
     fp = fp.to(cuda).train()
     u = uf.to(cuda).requires_grad_(True)
     o = fp(unknown.to(cuda), known.to(cuda), u, kf.to(cuda))
-    assert _max_norm_err(o.detach(), gold["fp_out"]) < 2e-2
+    np.testing.assert_allclose(o.detach().cpu().numpy(), gold["fp_out"], rtol=1e-3, atol=1e-4 * float(np.abs(gold["fp_out"]).max()))
     (o * det_tensor("w_fp", tuple(o.shape), 1.0).to(cuda)).sum().backward()
-    assert _max_norm_err(u.grad, gold["fp_grad_unknow_feats"]) < 4e-2
+    assert _rms_err(u.grad, gold["fp_grad_unknow_feats"]) < 2e-2
     for n, p in fp.named_parameters():
-        assert _max_norm_err(p.grad, gold["fp_grad_" + n]) < 4e-2, n
+        assert _rms_err(p.grad, gold["fp_grad_" + n]) < 2e-2, n
     for n, b in fp.named_buffers():
         if not n.endswith("num_batches_tracked"):
-            np.testing.assert_allclose(b.cpu().numpy(), gold["fp_buf_" + n], rtol=2e-3, atol=2e-4, err_msg=n)
+            np.testing.assert_allclose(b.cpu().numpy(), gold["fp_buf_" + n], rtol=1e-4, atol=1e-5, err_msg=n)
 
 
 def test_backbone_train_step_vs_reference_golden(pkg, gold, cuda):
     """One training step of the whole backbone (train-mode BatchNorm in all 16 layers, backward through FP and SA
-    layers, grouping / interpolation scatter-adds) against the reference's own Pointnet2Backbone."""
+    layers, grouping / interpolation scatter-adds) against the reference's own Pointnet2Backbone.
+
+    Sixteen batch-normalised layers deep, this synthetic network amplifies ANY rounding ~7x per SA level, and its
+    max-pool / ReLU gradients are discontinuous, so even two fp32 implementations disagree visibly at the end of the
+    chain.  The test therefore runs the step twice on the same GPU -- on the tcgen05 kernels and on torch's own
+    fp32 layers (TF32 off) -- and holds the tcgen05 path to the same distance from the reference's CPU result as
+    torch's fp32 layers reach (x2.5 slack, floors stated below)."""
     from make_golden_train import BB_PARAMS, BB_STATS, backbone_scene
-    bb = pkg.Pointnet2Backbone(input_feature_dim=1)
-    fill_state_dict(bb)
-    bb = bb.to(cuda).train()
-    d = bb({"point_clouds": backbone_scene().to(cuda)})
-    assert (d["fp2_inds"].cpu().numpy() == gold["bb_fp2_inds"]).all()
-    assert _max_norm_err(d["sa2_features"][:, ::8, ::16].detach(), gold["bb_sa2_features_sub"]) < 3e-2
-    assert _max_norm_err(d["fp2_features"][:, ::8, ::16].detach(), gold["bb_fp2_features_sub"]) < 3e-2
-    (d["fp2_features"] * det_tensor("w_bb", tuple(d["fp2_features"].shape), 1.0).to(cuda)).sum().backward()
-    named = dict(bb.named_parameters())
-    errs = {n: _max_norm_err(named[n].grad, gold["bb_grad_" + n]) for n in BB_PARAMS}
-    assert max(errs.values()) < 8e-2, errs
-    sd = bb.state_dict()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    res = {}
+    try:
+        for backend in ("tcgen05", "torch"):
+            bb = pkg.Pointnet2Backbone(input_feature_dim=1)
+            fill_state_dict(bb)
+            bb = bb.to(cuda).train()
+            with pkg.mlp_backend(backend):
+                d = bb({"point_clouds": backbone_scene().to(cuda)})
+                assert (d["fp2_inds"].cpu().numpy() == gold["bb_fp2_inds"]).all()
+                fwd = {"sa2": _max_norm_err(d["sa2_features"][:, ::8, ::16].detach(), gold["bb_sa2_features_sub"]),
+                       "fp2": _max_norm_err(d["fp2_features"][:, ::8, ::16].detach(), gold["bb_fp2_features_sub"])}
+                (d["fp2_features"] * det_tensor("w_bb", tuple(d["fp2_features"].shape), 1.0).to(cuda)).sum().backward()
+            named = dict(bb.named_parameters())
+            sd = bb.state_dict()
+            res[backend] = (fwd, {n: _rms_err(named[n].grad, gold["bb_grad_" + n]) for n in BB_PARAMS},
+                            {n: _max_norm_err(sd[n], gold["bb_buf_" + n]) for n in BB_STATS})
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    ours, ref = res["tcgen05"], res["torch"]
+    print("backbone train step vs the reference's CPU result -- forward max-norm, gradient relative rms, running stats:")
+    print("  tcgen05 kernels :", ours)
+    print("  torch fp32 (GPU):", ref)
+    assert ours[0]["sa2"] < 1e-3 and ours[0]["fp2"] < max(2.5 * ref[0]["fp2"], 1e-2), ours[0]
+    for n in BB_PARAMS:
+        assert ours[1][n] < max(2.5 * ref[1][n], 2e-2), (n, ours[1][n], ref[1][n])
     for n in BB_STATS:
-        np.testing.assert_allclose(sd[n].cpu().numpy(), gold["bb_buf_" + n], rtol=5e-3, atol=5e-4, err_msg=n)
+        assert ours[2][n] < max(2.5 * ref[2][n], 1e-3), (n, ours[2][n], ref[2][n])
