@@ -343,6 +343,69 @@ def grounding_leg(torch, dist, pkg, syn, model, dev, dev_pool, host_pool, world,
                         " with the cross-GPU embedding all-gather" if world > 1 else " (single GPU: no collective)")}
 
 
+def train_step_leg(torch, dist, pkg, syn, dev, host_pool, world, rank, steps=5):
+    """BASELINE configs[2] as a TRAINING step, per rank 8 scenes x 40 000 points: VoteNetDetector in train() mode
+    (batch-statistics BatchNorm) -> vote / objectness / box / semantic-class losses + DIoU reference loss ->
+    backward -> Adam step.  Every shared MLP of the backbone and of the vote aggregation runs forward AND
+    backward on this repo's kernels (mlp_train.py: tcgen05 GEMMs with split-bf16 operands, own BatchNorm /
+    max-pool kernels); sampling, grouping, interpolation and nn_distance are the same kernels as in eval.  The
+    Conv1d heads of VotingModule / ProposalModule (built for eval only) use torch layers.
+    Replicas are independent (the reference trains with DataParallel; BatchNorm statistics stay per GPU): no
+    gradient collective is timed."""
+    import types
+    LD = importlib.import_module("3dvlp_b200.loss_detection")
+    LG = importlib.import_module("3dvlp_b200.loss_grounding")
+    msa = syn.mean_size_arr()
+    torch.manual_seed(45)
+    det = pkg.VoteNetDetector(input_feature_dim=C_IN, mean_size_arr=msa).to(dev).train()
+    cfg = types.SimpleNamespace(num_class=18, num_heading_bin=1, num_size_cluster=18, mean_size_arr=msa,
+                                mean_size_arr_tensor=torch.from_numpy(msa).to(dev))
+    opt = torch.optim.Adam(det.parameters(), lr=1e-3)
+    pc = host_pool[0].to(dev)
+    labels = {k: v.to(dev) for k, v in syn.make_labels(host_pool[0], seed=100 + rank, lang_num_max=8).items()}
+    g = torch.Generator().manual_seed(300 + rank)
+    cluster_ref = torch.randn(SCENES_PER_GPU * 8, 256, generator=g).to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        d = det({"point_clouds": pc})
+        d.update(labels)
+        d.update({"epoch": 10, "istrain": 1, "random": 0.7, "cluster_ref": cluster_ref})
+        d = LD.get_detection_loss(d, cfg)
+        d, ref_loss, _, _ = LG.compute_diou_loss(d, cfg)
+        loss = d["vote_loss"] + 0.1 * d["objectness_loss"] + d["box_loss"] + 0.3 * ref_loss + d["diou_loss"]
+        loss.backward()
+        opt.step()
+        return loss
+
+    losses = []
+    for _ in range(2):
+        losses.append(float(step()))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.reset_peak_memory_stats(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    losses.append(float(loss))
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    mlp = importlib.import_module("3dvlp_b200.mlp_train")
+    return {"value": SCENES_PER_GPU * world / (ms * 1e-3), "unit": "scenes/s", "ms_per_step": ms, "steps": steps,
+            "loss_first_last_rank0": [losses[0], losses[-1]], "operand_precision": mlp._PRECISION[0],
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+            "what": "TRAINING step of BASELINE configs[2]: detector forward in train() mode + detection / DIoU losses + "
+                    "backward + Adam, eager, 8 scenes x 40000 pts per GPU; shared MLPs forward and backward on own "
+                    "tcgen05 kernels"}
+
+
 def algorithmic_work():
     """Algorithmic bytes (HBM-bound ops) or FLOPs (tensor ops) per C-ABI call of one backbone forward on
     8 scenes x 40 000 points, C_in = 1 -- SURVEY.md section 8(d) / BASELINE.md section 4, keyed by
@@ -550,6 +613,12 @@ def main():
         if world > 1:
             raise
         grounding = {"error": repr(ex)[:300]}
+    try:
+        train_step = train_step_leg(torch, dist, pkg, syn, dev, host_pool, world, rank)
+    except Exception as ex:
+        if world > 1:
+            raise
+        train_step = {"error": repr(ex)[:300]}
     scenes = SCENES_PER_GPU * world * args.steps
     value = scenes / (ms * 1e-3)
     e2e_value = scenes / (ms_e2e * 1e-3)
@@ -629,6 +698,7 @@ def main():
                                      "timed graphs captured (%s); shares are of the SERIALISED per-op sum, not of the "
                                      "pipelined step" % json.dumps(graphs[0].options)}
         line["grounding_step_forward"] = grounding
+        line["train_step"] = train_step
         if world == 1:
             try:
                 line["ref_cuda_ext"] = reference_cuda_ext_leg(torch, pkg, model, dev_pool, min(args.steps, 5))
