@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib3dvlp_b200.so")
+LIB_PATH = os.environ.get("PN2_LIB_PATH") or os.path.join(_HERE, "lib3dvlp_b200.so")  # override: A/B builds of the kernels
 
 _lib = None
 

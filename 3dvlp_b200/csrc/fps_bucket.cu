@@ -23,6 +23,8 @@
 //               up to KMAX new centres.
 // Work per sample drops from N distance updates to ~0.5 k, and a scene needs 1 SM instead of 16, so a
 // batch no longer monopolises the GPU: other kernels and other batches run beside it.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pn2 {
@@ -32,11 +34,14 @@ constexpr int FB_THREADS = 1024;
 constexpr int FB_WARPS = 32;
 constexpr int FB_KMAX = 16;       // centres accepted per round at most
 constexpr int FB_CELLS = 8192;    // sort grid: 32 x 32 (Morton) x 8
-constexpr int FB_BK = 64;         // points per bucket (two per lane)
+// Points per bucket = 32 * PPL (PPL points per lane).  Scenes of up to 50 176 points use PPL = 2 with the running
+// minima in shared memory; larger scenes (up to 131 072 points: thread = bucket caps the buckets at 1024) use
+// PPL = 4 with the minima in an L2-resident global scratch (GT), fetched together with the bucket's points.
 
 struct FbArgs {
   const float* xyz;   // (b, n, 3)
   float4* sorted;     // (b, npad) scratch
+  float* temps_g;     // (b, npad) running minima when they do not fit shared memory, else nullptr
   int* idxs;          // (b, m)
   float* new_xyz;     // (b, m, 3) or nullptr
   int n, m, log2bs, nb, npad;
@@ -69,7 +74,9 @@ __device__ __forceinline__ int warp_argmax2(int& v, uint32_t& k) {
   return __ffs(win) - 1;
 }
 
+template <int PPL, bool GT>
 __global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs a) {
+  constexpr int FB_BK = 32 * PPL;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ float4 ctr[FB_KMAX];     // accepted centres (x, y, z, key bits)
   __shared__ int ctr_count;
@@ -87,11 +94,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs 
   int* __restrict__ idxs = a.idxs + static_cast<size_t>(scene) * m;
   float* __restrict__ oxyz = a.new_xyz ? a.new_xyz + static_cast<size_t>(scene) * m * 3 : nullptr;
 
-  float* temps = reinterpret_cast<float*>(smem_raw);                 // npad
-  float4* bb_a = reinterpret_cast<float4*>(temps + npad);            // nb: {max temp, key bits, x, y}
+  float* temps = GT ? a.temps_g + static_cast<size_t>(scene) * npad : reinterpret_cast<float*>(smem_raw);  // npad
+  // bucket records: behind the minima in shared memory, or (GT) at its start -- the sort's histogram, which
+  // aliases this region, is dead by the time they are first written
+  float4* bb_a = GT ? reinterpret_cast<float4*>(smem_raw) : reinterpret_cast<float4*>(reinterpret_cast<float*>(smem_raw) + npad);  // nb: {max temp, key bits, x, y}
   float2* bb_b = reinterpret_cast<float2*>(bb_a + nb);               // nb: {z, second temp}
   uint32_t* work = reinterpret_cast<uint32_t*>(bb_b + nb);           // nb: bucket | centre mask << 16
-  int* hist = reinterpret_cast<int*>(smem_raw);                      // aliases temps during the sort
+  int* hist = reinterpret_cast<int*>(smem_raw);                      // aliases temps / the records during the sort
   int* cursor = hist + FB_CELLS;
 
   const uint32_t bsmask = (1u << log2bs) - 1u;
@@ -178,40 +187,49 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs 
     __syncthreads();  // the CTA's own global writes are visible to all its threads from here on
   }
 
-  // one bucket (64 points, two per lane): apply the centres in `mask`, refresh temps and the record
-  auto process_bucket = [&](int b, uint32_t mask, bool init, const float4& p0, const float4& p1) {
-    const int k0 = b * FB_BK + lane, k1 = k0 + 32;
-    const int o0 = __float_as_int(p0.w), o1 = __float_as_int(p1.w);
-    float t0, t1;
-    if (init) {
-      // sampling_gpu.cu:105-106: `if (mag <= 1e-3) continue;` -- a double comparison
-      const float m0 = __fmaf_rn(p0.z, p0.z, __fmaf_rn(p0.x, p0.x, __fmul_rn(p0.y, p0.y)));
-      const float m1 = __fmaf_rn(p1.z, p1.z, __fmaf_rn(p1.x, p1.x, __fmul_rn(p1.y, p1.y)));
-      t0 = (o0 >= 0 && !(static_cast<double>(m0) <= 1e-3)) ? 1e10f : -1.f;
-      t1 = (o1 >= 0 && !(static_cast<double>(m1) <= 1e-3)) ? 1e10f : -1.f;
-    } else {
-      t0 = temps[k0]; t1 = temps[k1];
+  // one bucket (32 * PPL points, PPL per lane): apply the centres in `mask`, refresh temps and the record.
+  // `tin` = the running minima of the lane's points (ignored when `init`).
+  auto process_bucket = [&](int b, uint32_t mask, bool init, const float4 (&p)[PPL], const float (&tin)[PPL]) {
+    float t[PPL];
+    int o[PPL];
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) {
+      o[q] = __float_as_int(p[q].w);
+      if (init) {
+        // sampling_gpu.cu:105-106: `if (mag <= 1e-3) continue;` -- a double comparison
+        const float mg = __fmaf_rn(p[q].z, p[q].z, __fmaf_rn(p[q].x, p[q].x, __fmul_rn(p[q].y, p[q].y)));
+        t[q] = (o[q] >= 0 && !(static_cast<double>(mg) <= 1e-3)) ? 1e10f : -1.f;
+      } else {
+        t[q] = GT ? tin[q] : temps[b * FB_BK + 32 * q + lane];  // shared memory: read on the spot; global: prefetched
+      }
     }
     while (mask) {
       const int c = __ffs(mask) - 1;
       mask &= mask - 1;
-      const float4 o = ctr[c];
-      t0 = fminf(sqdist3(p0.x - o.x, p0.y - o.y, p0.z - o.z), t0);
-      t1 = fminf(sqdist3(p1.x - o.x, p1.y - o.y, p1.z - o.z), t1);
+      const float4 oc = ctr[c];
+#pragma unroll
+      for (int q = 0; q < PPL; ++q) t[q] = fminf(sqdist3(p[q].x - oc.x, p[q].y - oc.y, p[q].z - oc.z), t[q]);
     }
-    temps[k0] = t0; temps[k1] = t1;
-    // lane-local best of the two points (value, then smaller key), the other one is the lane's rest
-    const uint32_t u0 = static_cast<uint32_t>(o0), u1 = static_cast<uint32_t>(o1);
-    const uint32_t key0 = o0 >= 0 ? ((log2bs ? __brev(u0 & bsmask) : 0u) | (u0 >> log2bs)) : 0xffffffffu;
-    const uint32_t key1 = o1 >= 0 ? ((log2bs ? __brev(u1 & bsmask) : 0u) | (u1 >> log2bs)) : 0xffffffffu;
-    const int v0 = __float_as_int(t0), v1 = __float_as_int(t1);  // t >= 0 or exactly -1: int order ok
-    const bool first1 = v1 > v0 || (v1 == v0 && key1 < key0);
-    const int vb = first1 ? v1 : v0, vrest = first1 ? v0 : v1;
-    const uint32_t key = first1 ? key1 : key0;
-    const float bx = first1 ? p1.x : p0.x, by = first1 ? p1.y : p0.y, bz = first1 ? p1.z : p0.z;
-    const float rx = first1 ? p0.x : p1.x, ry = first1 ? p0.y : p1.y, rz = first1 ? p0.z : p1.z;
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) temps[b * FB_BK + 32 * q + lane] = t[q];
+    // lane-local best of its points: value, then smaller key
+    int v[PPL];
+    uint32_t key[PPL];
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) {
+      const uint32_t u = static_cast<uint32_t>(o[q]);
+      key[q] = o[q] >= 0 ? ((log2bs ? __brev(u & bsmask) : 0u) | (u >> log2bs)) : 0xffffffffu;
+      v[q] = __float_as_int(t[q]);  // t >= 0 or exactly -1: int order ok
+    }
+    int vb = v[0];
+    uint32_t kb = key[0];
+    float bx = p[0].x, by = p[0].y, bz = p[0].z;
+#pragma unroll
+    for (int q = 1; q < PPL; ++q) {
+      if (v[q] > vb || (v[q] == vb && key[q] < kb)) { vb = v[q]; kb = key[q]; bx = p[q].x; by = p[q].y; bz = p[q].z; }
+    }
     const int vmax = __reduce_max_sync(0xffffffffu, vb);
-    const uint32_t kk = (vb == vmax) ? key : 0xffffffffu;
+    const uint32_t kk = (vb == vmax) ? kb : 0xffffffffu;
     const uint32_t kmin = __reduce_min_sync(0xffffffffu, kk);
     const bool win = (kk == kmin) && (vb == vmax);
     const int first = __ffs(__ballot_sync(0xffffffffu, win)) - 1;  // unique unless the bucket is empty
@@ -224,18 +242,34 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs 
     const float wx = __shfl_sync(0xffffffffu, bx, first), wy = __shfl_sync(0xffffffffu, by, first),
                 wz = __shfl_sync(0xffffffffu, bz, first);
     const int none = __float_as_int(-1.f);
-    const bool twin_b = (vb == vmax) && (bx == wx) && (by == wy) && (bz == wz);     // incl. the winner
-    const bool twin_r = (vrest == vmax) && (rx == wx) && (ry == wy) && (rz == wz);
-    const int sec = __reduce_max_sync(0xffffffffu, max(twin_b ? none : vb, twin_r ? none : vrest));
+    int rest = none;
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) {
+      const bool twin = (v[q] == vmax) && (p[q].x == wx) && (p[q].y == wy) && (p[q].z == wz);  // incl. the winner
+      rest = max(rest, twin ? none : v[q]);
+    }
+    const int sec = __reduce_max_sync(0xffffffffu, rest);
     if (lane == first) {
       bb_a[b] = make_float4(__int_as_float(vmax), __uint_as_float(kmin), bx, by);
       bb_b[b] = make_float2(bz, __int_as_float(sec));
     }
   };
+  auto load_bucket = [&](int b, float4 (&p)[PPL], float (&t)[PPL], bool with_temps) {
+    const float4* src = sorted + b * FB_BK + lane;
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) {
+      p[q] = src[32 * q];
+      t[q] = (GT && with_temps) ? temps[b * FB_BK + 32 * q + lane] : 0.f;
+    }
+  };
 
   // ================= init: temps, bucket records, bucket and group boxes ==========================
-  for (int b = warp; b < nb; b += FB_WARPS)
-    process_bucket(b, 0u, true, sorted[b * FB_BK + lane], sorted[b * FB_BK + 32 + lane]);
+  for (int b = warp; b < nb; b += FB_WARPS) {
+    float4 p[PPL];
+    float t[PPL];
+    load_bucket(b, p, t, false);
+    process_bucket(b, 0u, true, p, t);
+  }
   // thread = bucket, warp = group of GB consecutive buckets.  GB = ceil(nb / 32) spreads the buckets over
   // all 32 warps: every warp reports a candidate to the acceptance step (32 instead of nb / 32), and the
   // bound -- the best value no group reported -- comes from smaller groups, so more samples are
@@ -313,21 +347,25 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs 
     const int nw = nwork;
     {
       uint32_t item = 0u;
-      float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+      float4 pn[PPL];
+      float tn[PPL];
+#pragma unroll
+      for (int q = 0; q < PPL; ++q) { pn[q] = make_float4(0.f, 0.f, 0.f, 0.f); tn[q] = 0.f; }
       if (warp < nw) {
         item = work[warp];
-        const float4* src = sorted + (item & 0xffffu) * FB_BK + lane;
-        p0 = src[0]; p1 = src[32];
+        load_bucket(static_cast<int>(item & 0xffffu), pn, tn, true);
       }
       for (int i = warp; i < nw; i += FB_WARPS) {
         const uint32_t cur = item;
-        const float4 c0 = p0, c1 = p1;
-        if (i + FB_WARPS < nw) {
+        float4 pc[PPL];
+        float tcur[PPL];
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) { pc[q] = pn[q]; tcur[q] = tn[q]; }
+        if (i + FB_WARPS < nw) {  // a bucket appears once per round: its minima cannot change under the prefetch
           item = work[i + FB_WARPS];
-          const float4* src = sorted + (item & 0xffffu) * FB_BK + lane;
-          p0 = src[0]; p1 = src[32];
+          load_bucket(static_cast<int>(item & 0xffffu), pn, tn, true);
         }
-        process_bucket(static_cast<int>(cur & 0xffffu), cur >> 16, false, c0, c1);
+        process_bucket(static_cast<int>(cur & 0xffffu), cur >> 16, false, pc, tcur);
       }
     }
     __syncthreads();
@@ -429,31 +467,48 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs 
 
 }  // namespace
 
-// Largest scene the single-CTA kernel holds on chip: 4 B/point of running minima + 28 B per 64-point bucket
-// within the 227 KB of shared memory of an sm_100a CTA.
-bool fps_bucket_supported(int n) { return n >= 16384 && n <= 50176; }
+// Scenes of up to 50 176 points keep the running minima on chip (4 B/point + 28 B per 64-point bucket within the
+// 227 KB of shared memory of an sm_100a CTA); up to 131 072 points (1024 buckets of 128) the minima live in an
+// L2-resident scratch and only the bucket records stay in shared memory.
+constexpr int kSmemPoints = 50176, kMaxPoints = 131072;
+bool fps_bucket_supported(int n) { return n >= 16384 && n <= kMaxPoints; }
 
 int fps_bucket_run(int b, int n, int m, int log2bs, const float* dataset, int* idxs, float* new_xyz,
                    cudaStream_t stream) {
   FbArgs a;
   a.xyz = dataset; a.idxs = idxs; a.new_xyz = new_xyz;
   a.n = n; a.m = m; a.log2bs = log2bs;
-  a.nb = (n + FB_BK - 1) / FB_BK;
-  a.npad = a.nb * FB_BK;
+  const bool big = n > kSmemPoints;
+  const int bk = big ? 128 : 64;
+  a.nb = (n + bk - 1) / bk;
+  a.npad = a.nb * bk;
   PN2_REQUIRE(a.nb <= FB_THREADS, "fps_bucket: too many buckets");
-  const size_t smem = static_cast<size_t>(a.npad) * 4 + static_cast<size_t>(a.nb) * (16 + 8 + 4) + 64;
-  PN2_REQUIRE(smem <= 227 * 1024 && static_cast<size_t>(a.npad) * 4 >= 2 * FB_CELLS * sizeof(int),
+  const size_t records = static_cast<size_t>(a.nb) * (16 + 8 + 4) + 64;
+  const size_t sort_bytes = 2 * FB_CELLS * sizeof(int);
+  const size_t smem = big ? (records > sort_bytes ? records : sort_bytes) : static_cast<size_t>(a.npad) * 4 + records;
+  PN2_REQUIRE(smem <= 227 * 1024 && (big || static_cast<size_t>(a.npad) * 4 >= sort_bytes),
               "fps_bucket: n=%d outside the supported range", n);
-  float4* sorted = nullptr;
-  PN2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sorted), static_cast<size_t>(b) * a.npad * sizeof(float4), stream));
-  a.sorted = sorted;
-  cudaError_t e = cudaFuncSetAttribute(fps_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
-  if (e == cudaSuccess) {
-    fps_bucket_kernel<<<b, FB_THREADS, smem, stream>>>(a);
-    e = cudaGetLastError();
+  uint8_t* ws = nullptr;
+  const size_t sorted_bytes = static_cast<size_t>(b) * a.npad * sizeof(float4);
+  const size_t temps_bytes = big ? static_cast<size_t>(b) * a.npad * sizeof(float) : 0;
+  PN2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), sorted_bytes + temps_bytes, stream));
+  a.sorted = reinterpret_cast<float4*>(ws);
+  a.temps_g = big ? reinterpret_cast<float*>(ws + sorted_bytes) : nullptr;
+  cudaError_t e;
+  if (big) {
+    e = cudaFuncSetAttribute(fps_bucket_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) {
+      fps_bucket_kernel<4, true><<<b, FB_THREADS, smem, stream>>>(a);
+      e = cudaGetLastError();
+    }
+  } else {
+    e = cudaFuncSetAttribute(fps_bucket_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) {
+      fps_bucket_kernel<2, false><<<b, FB_THREADS, smem, stream>>>(a);
+      e = cudaGetLastError();
+    }
   }
-  cudaFreeAsync(sorted, stream);
+  cudaFreeAsync(ws, stream);
   if (e != cudaSuccess) return cuda_fail(e, "fps_bucket_kernel");
   return PN2_OK;
 }

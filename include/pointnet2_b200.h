@@ -44,7 +44,7 @@ int pn2_poll_device_error(int* flag_out, void* stream);
  * Returns -1 for an unknown name. */
 long long pn2_get_stat(const char* name);
 /* Run-time options (process-wide; initial value from the environment variable in brackets):
- *   "fps_bucket" [PN2_FPS_BUCKET, default 0]  1 = large scenes (16 384..50 176 points) use the single-SM
+ *   "fps_bucket" [PN2_FPS_BUCKET, default 0]  1 = large scenes (16 384..131 072 points) use the single-SM
  *                bucketed FPS kernel with spatial pruning instead of the 16-SM cluster kernel: same
  *                output, ~2x the latency of one batch, 1/16 of the SM footprint (throughput mode);
  *   "bq_grid"    [PN2_BQ_GRID, default 1]     0 = ball query always uses the linear scan;

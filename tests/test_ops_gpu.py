@@ -50,11 +50,17 @@ FPS_CASES = {
     "bucket_40000_dups": (lambda: cloud(27, 1, 40000, extent=4.0, dup_frac=0.4, origin_pts=9)[..., :3].contiguous(), 2048),
     "bucket_lattice_39304": (lambda: _lattice(34), 1200),
     "bucket_50176_max": (lambda: cloud(28, 1, 50176, extent=5.0, dup_frac=0.1)[..., :3].contiguous(), 1024),
+    # above 50 176 points the bucketed kernel keeps its running minima in an L2-resident scratch (128-point buckets)
+    "bucket_50177_dups": (lambda: cloud(29, 1, 50177, extent=5.0, dup_frac=0.3, origin_pts=5)[..., :3].contiguous(), 700),
+    "bucket_lattice_97336": (lambda: _lattice(46), 900),
+    "bucket_100000_dups": (lambda: cloud(30, 2, 100000, extent=6.0, dup_frac=0.4, origin_pts=11)[..., :3].contiguous(), 1024),
+    "bucket_131072_max": (lambda: cloud(31, 1, 131072, extent=7.0)[..., :3].contiguous(), 512),
+    "bucket_all_origin_70000": (lambda: (cloud(32, 1, 70000)[..., :3] * 0.004).contiguous(), 40),
 }
 
 
 def _bucket_range(n):
-    return 16384 <= n <= 50176  # fps_bucket_supported (csrc/fps_bucket.cu)
+    return 16384 <= n <= 131072  # fps_bucket_supported (csrc/fps_bucket.cu)
 
 
 def _fps_variants(name):
@@ -102,7 +108,7 @@ def test_fps_bit_exact(pkg, oracle, cuda, name, bucket):
     assert torch.equal(new_xyz.cpu(), ref_xyz)
 
 
-@pytest.mark.parametrize("n,bucket", [(900, 0), (9000, 0), (20000, 0), (20000, 1), (40000, 1)])
+@pytest.mark.parametrize("n,bucket", [(900, 0), (9000, 0), (20000, 0), (20000, 1), (40000, 1), (90000, 1)])
 def test_fps_nan_inf_coordinates(pkg, oracle, cuda, n, bucket):
     x = cloud(10, 1, n)[..., :3].contiguous()
     x[0, 17, 1] = float("nan"); x[0, 400] = float("inf"); x[0, 555, 2] = float("-inf")
