@@ -279,7 +279,10 @@ def backbone_forward(bb, data_dict):
                        data_dict["sa4_features"], nn=nn1)
     if feats is None:
         feats = bb.fp1(data_dict["sa3_xyz"], data_dict["sa4_xyz"], data_dict["sa3_features"], data_dict["sa4_features"])
-    up = fp_forward(bb.fp2, data_dict["sa2_xyz"], data_dict["sa3_xyz"], data_dict["sa2_features"], feats, nn=nn2)
+    # "_fp2_features_out": an optional caller-provided (B, 256, num_seed) fp32 buffer for the final features
+    # (GraphedBackbone(pack=...) points it into the buffer that leaves the device in one copy)
+    up = fp_forward(bb.fp2, data_dict["sa2_xyz"], data_dict["sa3_xyz"], data_dict["sa2_features"], feats, nn=nn2,
+                    out=data_dict.get("_fp2_features_out"))
     feats = up if up is not None else bb.fp2(data_dict["sa2_xyz"], data_dict["sa3_xyz"], data_dict["sa2_features"], feats)
     data_dict["fp2_features"] = feats
     data_dict["fp2_xyz"] = data_dict["sa2_xyz"]
@@ -321,7 +324,7 @@ def fp_neighbours(unknown, known):
     return idx, w
 
 
-def fp_forward(module, unknown, known, unknow_feats, known_feats, nn=None):
+def fp_forward(module, unknown, known, unknow_feats, known_feats, nn=None, out=None):
     """PointnetFPModule.forward (pointnet2_modules.py:371-416) in 1 + n_layers launches: the fused
     three_nn/interpolate/concat front end, then one tcgen05 linear kernel per MLP layer (the last
     one stores straight into the reference's (B, C, n) layout)."""
@@ -354,5 +357,5 @@ def fp_forward(module, unknown, known, unknow_feats, known_feats, nn=None):
         if i < last:
             x = tcm.linear(x, w, bias, relu=True, out="bf16")
         else:
-            x = tcm.linear(x, w, bias, relu=True, out="cm", rows_per_batch=n)
+            x = tcm.linear(x, w, bias, relu=True, out="cm", rows_per_batch=n, y=out)
     return x

@@ -18,7 +18,7 @@ class GraphedBackbone:
     next call.  Falls back to eager execution (``self.graph is None``) if capture is not possible.
     """
 
-    def __init__(self, backbone, example_batch, warmup=3, throughput=False, priority=0):
+    def __init__(self, backbone, example_batch, warmup=3, throughput=False, priority=0, pack=None):
         if backbone.training:
             raise RuntimeError("GraphedBackbone needs the backbone in eval() mode")
         if not example_batch.is_cuda or example_batch.dtype != torch.float32:
@@ -39,6 +39,7 @@ class GraphedBackbone:
             self.graph = None
             self.static_out = None
             self.capture_error = None
+            self.packed, self.pack_layout = None, None
             cur = torch.cuda.current_stream(self.static_in.device)
             # `priority` (0 = default, negative = higher): every kernel of the graph is captured on streams
             # of that priority and keeps it on replay.  A serving loop with several graphs in flight gives
@@ -54,12 +55,45 @@ class GraphedBackbone:
             torch.cuda.synchronize(self.static_in.device)
             try:
                 g = torch.cuda.CUDAGraph()
+                inputs = {"point_clouds": self.static_in}
+                if pack:
+                    # `pack` = the backbone outputs a serving loop reads back every step (fp2_features, fp2_xyz,
+                    # fp2_inds): they live in ONE contiguous byte buffer, so the host issues one device->host
+                    # copy per step instead of one per tensor.  The final linear kernel writes fp2_features
+                    # straight into its slice; the two small tensors are placed by elementwise kernels (a
+                    # device-to-device memcpy node would queue behind the PCIe traffic on the copy engines).
+                    with torch.no_grad():
+                        probe = backbone({"point_clouds": self.static_in})
+                    self.pack_layout, off = [], 0
+                    for k in pack:
+                        nbytes = probe[k].numel() * probe[k].element_size()
+                        self.pack_layout.append((k, off, nbytes, tuple(probe[k].shape), probe[k].dtype))
+                        off += (nbytes + 255) // 256 * 256
+                    del probe
+                    torch.cuda.synchronize(self.static_in.device)
+                    self.packed = torch.empty(off, device=self.static_in.device, dtype=torch.uint8)
+                    views = self.packed_views(self.packed)
+                    if "fp2_features" in views:
+                        inputs["_fp2_features_out"] = views["fp2_features"]
                 with torch.no_grad(), torch.cuda.graph(g, stream=s):
-                    out = backbone({"point_clouds": self.static_in})
+                    out = backbone(inputs)
+                    if pack:
+                        for k, v in views.items():
+                            if out[k].data_ptr() == v.data_ptr():
+                                continue  # written in place by the producing kernel
+                            if v.dtype.is_floating_point:
+                                torch.mul(out[k], 1.0, out=v)
+                            else:
+                                torch.bitwise_or(out[k], 0, out=v)
                 self.graph, self.static_out = g, out
             except Exception as ex:  # pragma: no cover - depends on driver behaviour
                 self.capture_error = repr(ex)
                 torch.cuda.synchronize(self.static_in.device)
+
+    def packed_views(self, buf):
+        """The tensors of `pack` as views into `buf`, a byte buffer laid out like self.packed (e.g. the pinned
+        host buffer the serving loop copied it into)."""
+        return {k: buf[o:o + nbytes].view(dt).view(shape) for k, o, nbytes, shape, dt in self.pack_layout}
 
     def check(self):
         """Synchronise and raise Pn2Error if a kernel of this device bailed out of a bounded wait since the

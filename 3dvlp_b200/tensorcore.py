@@ -45,7 +45,7 @@ def pack_point_rows(pc, col0, c, kpad=None):
     return out
 
 
-def linear(x, w, bias=None, relu=False, out="f32", rows_per_batch=0):
+def linear(x, w, bias=None, relu=False, out="f32", rows_per_batch=0, y=None):
     """act(x @ W^T + bias) on tensor cores.  x (M, kpad) bf16; w PackedWeight; out in
     {"f32": (M,n) fp32, "bf16": (M,n) bf16, "cm": (M/rows_per_batch, n, rows_per_batch) fp32}."""
     L.require_cuda_path(x)
@@ -53,7 +53,12 @@ def linear(x, w, bias=None, relu=False, out="f32", rows_per_batch=0):
         raise RuntimeError("linear: x must be a contiguous bf16 (M, %d) tensor" % w.kpad)
     m = x.shape[0]
     mode = {"f32": 0, "bf16": 1, "cm": 2}[out]
-    if mode == 0:
+    if y is not None:  # caller-provided output (e.g. a view into a buffer that leaves the device in one copy)
+        want = {0: ((m, w.n), torch.float32), 1: ((m, w.n), torch.bfloat16),
+                2: ((m // max(rows_per_batch, 1), w.n, rows_per_batch), torch.float32)}[mode]
+        if tuple(y.shape) != want[0] or y.dtype != want[1] or not y.is_contiguous() or y.device != x.device:
+            raise RuntimeError("linear: y must be a contiguous %s tensor of shape %s" % (want[1], want[0]))
+    elif mode == 0:
         y = torch.empty(m, w.n, device=x.device, dtype=torch.float32)
     elif mode == 1:
         y = torch.empty(m, w.n, device=x.device, dtype=torch.bfloat16)

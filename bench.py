@@ -127,6 +127,41 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-rank runs: before any pinned allocation, restrict this rank to the host cores of its GPU's NUMA node
+    (where the cgroup's cpuset allows): its pinned buffers are then first-touched on that node and the
+    host<->device copies of the end-to-end loop stay off the socket interconnect.  Returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        node = None
+        for cand in (bus, bus[-12:]):
+            p = "/sys/bus/pci/devices/%s/numa_node" % cand
+            if os.path.exists(p):
+                node = int(open(p).read())
+                break
+        if node is None or node < 0:
+            return "gpu numa node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        want = cpus & allowed
+        if not want:
+            return "gpu on node %d, none of the %d allowed cores is (cpuset): not bound" % (node, len(allowed))
+        if want == allowed:
+            return "gpu on node %d, all %d allowed cores are too" % (node, len(allowed))
+        os.sched_setaffinity(0, want)
+        return "bound to %d of %d allowed cores on node %d" % (len(want), len(allowed), node)
+    except Exception as ex:
+        return "not bound (%s)" % repr(ex)[:80]
+
+
 def build_pool(torch, syn, dev, rank):
     """POOL batches of (8, 40000, 4): BASE_SCENES generated scenes re-used under seeded permutations of
     the point order (a different point order is a different FPS / ball-query problem)."""
@@ -376,7 +411,7 @@ def train_step_leg(torch, dist, pkg, syn, dev, host_pool, world, rank, steps=5):
         loss = d["vote_loss"] + 0.1 * d["objectness_loss"] + d["box_loss"] + 0.3 * ref_loss + d["diou_loss"]
         loss.backward()
         opt.step()
-        return loss
+        return loss.detach()
 
     losses = []
     for _ in range(2):
@@ -483,6 +518,7 @@ def main():
     L = pkg._lib
     L.lib()  # fail loudly now if the CUDA library is missing
 
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not bound"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -572,21 +608,18 @@ def main():
     # device->host reads queue up behind the last kernel; with descending lane priorities (kernels keep the
     # priority of the stream their graph was captured on) batches complete one after the other and the reads
     # of the early ones travel under the compute of the late ones (measured at K = 20: 16.1k -> 19.0k scenes/s)
-    if stagger:
-        e_graphs = [pkg.GraphedBackbone(model, dev_pool[0], throughput=throughput_mode, priority=lane_priority(k))
-                    for k in range(depth)]
-        e_lanes = [torch.cuda.Stream(device=dev, priority=lane_priority(k)) for k in range(depth)]
-    else:
-        e_graphs, e_lanes = graphs, lanes
-    d = graphed(dev_pool[0])
+    # The step's result (fp2_features / fp2_xyz / fp2_inds) is packed into one contiguous buffer inside the graph:
+    # the host issues ONE device->host copy per step (three calls per step: input copy, replay, output copy).
     outs = ("fp2_features", "fp2_xyz", "fp2_inds")
-    out_host = [{k: torch.empty(d[k].shape, dtype=d[k].dtype).pin_memory() for k in outs} for _ in range(depth)]
+    e_graphs = [pkg.GraphedBackbone(model, dev_pool[0], throughput=throughput_mode, priority=lane_priority(k), pack=outs)
+                for k in range(depth)]
+    e_lanes = [torch.cuda.Stream(device=dev, priority=lane_priority(k)) for k in range(depth)] if stagger else lanes
+    out_host = [torch.empty(g.packed.numel(), dtype=torch.uint8).pin_memory() for g in e_graphs]
     lane_of = {id(g): i for i, g in enumerate(e_graphs)}
 
     def e2e_step(g, s):
-        r = g(host_pool[s % POOL])  # pinned host -> static device input, then the graph
-        for k in outs:
-            out_host[lane_of[id(g)]][k].copy_(r[k], non_blocking=True)
+        g(host_pool[s % POOL])  # pinned host -> static device input, then the graph
+        out_host[lane_of[id(g)]].copy_(g.packed, non_blocking=True)
 
     run_steps(0, 3 * depth, e2e_step, e_graphs, e_lanes)   # untimed settling of the copy path (first use of the pinned buffers)
     torch.cuda.synchronize()
@@ -600,7 +633,10 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     graphs[0].check()  # raises if any kernel bailed out of a bounded wait during the timed regions
     h2d = dev_pool[0].numel() * 4
-    d2h = sum(v.numel() * v.element_size() for v in out_host[0].values())
+    d2h = sum(nbytes for _, _, nbytes, _, _ in e_graphs[0].pack_layout)
+    # the host copy of the last step of lane 0 holds what the device computed (views into the packed buffer)
+    last = e_graphs[0].packed_views(out_host[0])
+    assert torch.equal(last["fp2_inds"], e_graphs[0].static_out["fp2_inds"].cpu())
 
     # max over ranks, on-device timings
     if world > 1:
@@ -689,7 +725,7 @@ def main():
                         POOL, POOL * SCENES_PER_GPU * N_POINTS * 4 * (3 + C_IN) / 1e6),
                     "parallelism": "scene-sharded dp%d, no data-path collective" % world,
                     "execution": execution, "batches_in_flight": depth,
-                    "e2e_lane_priority_levels": levels,
+                    "e2e_lane_priority_levels": levels, "e2e_host_calls_per_step": 3, "numa": numa,
                     "fps_algorithm": "bucketed single-SM (throughput mode)" if throughput_mode else "16-CTA cluster (latency mode)"},
                 "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},

@@ -207,6 +207,34 @@ def test_graphed_backbone_replays_identically(pkg, cuda):
             assert torch.equal(v, want[k]), k
 
 
+def test_graphed_backbone_packed_outputs(pkg, cuda):
+    """GraphedBackbone(pack=...) places the outputs a serving loop reads back in ONE contiguous buffer (the last
+    linear kernel writes fp2_features straight into it): one device->host copy returns the same tensors."""
+    import importlib
+    from common import fill_state_dict
+    syn = importlib.import_module("3dvlp_b200.synthetic")
+    bb = pkg.Pointnet2Backbone(input_feature_dim=1)
+    fill_state_dict(bb)
+    bb = bb.to(cuda).eval()
+    a = syn.make_batch(0, 2, 9000, 1).to(cuda)
+    keys = ("fp2_features", "fp2_xyz", "fp2_inds")
+    g = pkg.GraphedBackbone(bb, a, pack=keys, priority=-1)
+    assert g.graph is not None, g.capture_error
+    host = torch.empty(g.packed.numel(), dtype=torch.uint8).pin_memory()
+    for pc in (syn.make_batch(5, 2, 9000, 1).to(cuda), a):
+        out = g(pc)
+        host.copy_(g.packed, non_blocking=True)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            want = bb({"point_clouds": pc.clone()})
+        views = g.packed_views(host)
+        for k in keys:
+            assert views[k].dtype == want[k].dtype and views[k].shape == want[k].shape
+            assert torch.equal(views[k], want[k].cpu()), k
+            assert torch.equal(out[k], want[k]), k
+    assert out["fp2_features"].data_ptr() == g.packed.data_ptr()  # written in place, no copy node
+
+
 @pytest.mark.parametrize("name", ["sa1_like", "sa2_like", "sa3_like", "sparse_balls_wide", "tiny"])
 def test_sa_tiles_per_group_option_is_bit_identical(pkg, cuda, name):
     """pn2_set_option("sa_tiles_per_group", k) only changes how many persistent CTAs share the tiles
