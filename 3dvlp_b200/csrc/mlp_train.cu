@@ -156,7 +156,7 @@ bn_relu_rows_kernel(long long rows, int c, int ld, const float* __restrict__ y, 
 }
 
 // out[b, ch, j] = max over the ns rows of group g = b * npoint + j of relu(y * scale + shift); arg-max = the FIRST
-// slot that attains it (F.max_pool2d: strict '>' scan)
+// slot that attains it (F.max_pool2d: strict '>' scan), stored point-major as argmax[g][ch]
 __global__ void __launch_bounds__(RT)
 bn_relu_maxpool_kernel(int groups, int ns, int c, int ld, int npoint, const float* __restrict__ y,
                        const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out_cm,
@@ -173,9 +173,8 @@ bn_relu_maxpool_kernel(int groups, int ns, int c, int ld, int npoint, const floa
     if (s == 0 || v > best) { best = v; bi = s; }
   }
   const int b = g / npoint, j = g - b * npoint;
-  const long long o = (static_cast<long long>(b) * c + ch) * npoint + j;
-  out_cm[o] = best;
-  argmax[o] = bi;
+  out_cm[(static_cast<long long>(b) * c + ch) * npoint + j] = best;
+  argmax[t] = bi;  // point-major (group, channel): coalesced here and in the backward kernels
 }
 
 // ---- backward ----------------------------------------------------------------------------------------
@@ -196,25 +195,24 @@ bn_bwd_stats_dense_kernel(long long rows, int c, int ld_da, int ld_y, long long 
 // pooled upstream: the gradient of group g reaches only its arg-max row; "rows" of the reduction are groups
 __global__ void __launch_bounds__(RT)
 bn_bwd_stats_pool_kernel(long long groups, int ns, int c, int ld_y, int npoint, long long groups_per_cta,
-                         const float* __restrict__ dout_cm, const int* __restrict__ argmax, const float* __restrict__ y,
+                         const float* __restrict__ dout_pm, const int* __restrict__ argmax, const float* __restrict__ y,
                          const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ invstd, double* __restrict__ s1, double* __restrict__ s2) {
   column_reduce2(groups, c, groups_per_cta, [&](long long g, int ch, float& a, float& b) {
-    const long long bb = g / npoint, j = g - bb * npoint;
-    const long long o = (bb * c + ch) * npoint + j;
+    const long long o = g * c + ch;  // upstream gradient and arg-max are point-major (group, channel)
     const long long r = g * ns + __ldg(argmax + o);
     const float yv = __ldg(y + r * ld_y + ch);
     const float act = __fmaf_rn(yv, __ldg(scale + ch), __ldg(shift + ch));
-    const float d = act > 0.f ? __ldg(dout_cm + o) : 0.f;
+    const float d = act > 0.f ? __ldg(dout_pm + o) : 0.f;
     a = d; b = d * (yv - __ldg(mean + ch)) * __ldg(invstd + ch);
   }, s1, s2);
 }
 
 // dY = gamma invstd (dYhat - (s1 + xhat s2) / count)  [count > 0: batch statistics]  or  gamma invstd dYhat
-// [count == 0: frozen statistics] -> bf16 rows.  Upstream dense (da) or pooled (dout_cm + argmax).
+// [count == 0: frozen statistics] -> bf16 rows.  Upstream dense (da) or pooled (dout_pm + argmax, point-major).
 __global__ void __launch_bounds__(RT)
 bn_bwd_rows_kernel(long long rows, int c, int ld_da, int ld_y, const float* __restrict__ da,
-                   const float* __restrict__ dout_cm, const int* __restrict__ argmax, int ns, int npoint,
+                   const float* __restrict__ dout_pm, const int* __restrict__ argmax, int ns, int npoint,
                    const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                    const double* __restrict__ s1, const double* __restrict__ s2, double count,
@@ -225,9 +223,9 @@ bn_bwd_rows_kernel(long long rows, int c, int ld_da, int ld_y, const float* __re
   const long long r = t / chunks;
   const int ch0 = static_cast<int>(t - r * chunks) << 3;
   const float inv_count = count > 0.0 ? static_cast<float>(1.0 / count) : 0.f;
-  long long g = 0, bb = 0, j = 0;
+  long long g = 0;
   int slot = 0;
-  if (!da) { g = r / ns; slot = static_cast<int>(r - g * ns); bb = g / npoint; j = g - bb * npoint; }
+  if (!da) { g = r / ns; slot = static_cast<int>(r - g * ns); }
   float o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -238,8 +236,8 @@ bn_bwd_rows_kernel(long long rows, int c, int ld_da, int ld_y, const float* __re
     if (da) {
       up = __ldg(da + r * ld_da + ch);
     } else {
-      const long long oo = (bb * c + ch) * npoint + j;
-      up = __ldg(argmax + oo) == slot ? __ldg(dout_cm + oo) : 0.f;
+      const long long oo = g * c + ch;
+      up = __ldg(argmax + oo) == slot ? __ldg(dout_pm + oo) : 0.f;
     }
     const float d = act > 0.f ? up : 0.f;
     const float is = __ldg(invstd + ch);
@@ -466,7 +464,7 @@ extern "C" int pn2_bn_relu_maxpool(int groups, int ns, int c, int ld, int npoint
   return PN2_OK;
 }
 
-extern "C" int pn2_bn_bwd_stats(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_cm,
+extern "C" int pn2_bn_bwd_stats(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_pm,
                                 const int* argmax, int ns, int npoint, const float* y, const float* scale,
                                 const float* shift, const float* mean, const float* invstd, double* s1, double* s2,
                                 void* stream) {
@@ -478,17 +476,17 @@ extern "C" int pn2_bn_bwd_stats(long long rows, int c, int ld_da, int ld_y, cons
     bn_bwd_stats_dense_kernel<<<static_cast<unsigned>((rows + per - 1) / per), RT, 0, as_stream(stream)>>>(
         rows, c, ld_da, ld_y, per, da, y, scale, shift, mean, invstd, s1, s2);
   } else {
-    PN2_REQUIRE(dout_cm && argmax && ns > 0 && npoint > 0 && rows % ns == 0, "bn_bwd_stats: pooled upstream needs dout / argmax");
+    PN2_REQUIRE(dout_pm && argmax && ns > 0 && npoint > 0 && rows % ns == 0, "bn_bwd_stats: pooled upstream needs dout / argmax");
     const long long groups = rows / ns;
     const long long per = pick_rows_per_cta(groups, c);
     bn_bwd_stats_pool_kernel<<<static_cast<unsigned>((groups + per - 1) / per), RT, 0, as_stream(stream)>>>(
-        groups, ns, c, ld_y, npoint, per, dout_cm, argmax, y, scale, shift, mean, invstd, s1, s2);
+        groups, ns, c, ld_y, npoint, per, dout_pm, argmax, y, scale, shift, mean, invstd, s1, s2);
   }
   PN2_CHECK_LAUNCH("bn_bwd_stats_kernel");
   return PN2_OK;
 }
 
-extern "C" int pn2_bn_bwd_rows(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_cm,
+extern "C" int pn2_bn_bwd_rows(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_pm,
                                const int* argmax, int ns, int npoint, const float* y, const float* scale,
                                const float* shift, const float* mean, const float* invstd, const float* gamma,
                                const double* s1, const double* s2, long long count, int terms, void* dy_bf16,
@@ -497,10 +495,10 @@ extern "C" int pn2_bn_bwd_rows(long long rows, int c, int ld_da, int ld_y, const
   if (rows <= 0) return PN2_OK;
   PN2_REQUIRE(c > 0 && c % 8 == 0 && y && scale && shift && mean && invstd && s1 && s2 && dy_bf16 && terms >= 1 && terms <= 3,
               "bn_bwd_rows: bad arguments");
-  PN2_REQUIRE(da || (dout_cm && argmax && ns > 0 && npoint > 0), "bn_bwd_rows: no upstream gradient");
+  PN2_REQUIRE(da || (dout_pm && argmax && ns > 0 && npoint > 0), "bn_bwd_rows: no upstream gradient");
   const long long total = rows * (c / 8);
   bn_bwd_rows_kernel<<<static_cast<unsigned>((total + RT - 1) / RT), RT, 0, as_stream(stream)>>>(
-      rows, c, ld_da, ld_y, da, dout_cm, argmax, ns, npoint, y, scale, shift, mean, invstd, gamma, s1, s2,
+      rows, c, ld_da, ld_y, da, dout_pm, argmax, ns, npoint, y, scale, shift, mean, invstd, gamma, s1, s2,
       static_cast<double>(count), static_cast<__nv_bfloat16*>(dy_bf16), terms);
   PN2_CHECK_LAUNCH("bn_bwd_rows_kernel");
   return PN2_OK;

@@ -172,7 +172,7 @@ class _SharedMLPMaxPool(Function):
                 kw = co
             else:
                 out = torch.empty(B, co, M, device=dev, dtype=torch.float32)
-                arg = torch.empty(B, co, M, device=dev, dtype=torch.int32)
+                arg = torch.empty(B * M, co, device=dev, dtype=torch.int32)   # point-major (group, channel)
                 L.call("pn2_bn_relu_maxpool", B * M, S, co, co, M, L.ptr(Y), L.ptr(aff[0]), L.ptr(aff[1]), L.ptr(out),
                        L.ptr(arg), st, device=dev)
         ctx.save_for_backward(arg, *xs, *ys, *affine, *params)
@@ -188,7 +188,7 @@ class _SharedMLPMaxPool(Function):
         dev = dout.device
         P = B * M * S
         st = L.stream_of(dout)
-        dout = dout.contiguous().float()
+        dout = dout.float().transpose(1, 2).contiguous()   # (B, M, C): point-major like the arg-max
         grads = [None] * (3 * n)
         da, ld_da = None, 0
         grad_x = None

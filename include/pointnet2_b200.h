@@ -292,14 +292,16 @@ int pn2_pack_rows_split_bf16(int b, int c, int n, int kpad, int terms, const flo
                              void* stream);
 
 /* Last layer: out_cm[b][ch][j] = max over the ns rows of group g = b*npoint + j of relu(y*scale + shift)
- * (fp32, the reference's (B, C, npoint) layout) and argmax[b][ch][j] = the first slot attaining it. */
+ * (fp32, the reference's (B, C, npoint) layout) and argmax[g][ch] = the first slot attaining it (int32,
+ * point-major (groups, c)). */
 int pn2_bn_relu_maxpool(int groups, int ns, int c, int ld, int npoint, const float* y, const float* scale,
                         const float* shift, float* out_cm, int* argmax, void* stream);
 
 /* s1[ch] += sum dYhat, s2[ch] += sum dYhat * xhat over the rows, dYhat = upstream * [y*scale+shift > 0],
  * xhat = (y - mean) * invstd.  Upstream: dense `da` (rows, ld_da) fp32, or (da == NULL) the pooled gradient
- * dout_cm (B, c, npoint) routed to the arg-max slot of each group of ns rows. */
-int pn2_bn_bwd_stats(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_cm,
+ * dout_pm (groups, c) fp32 POINT-major (the transpose of the (B, c, npoint) gradient), routed to the arg-max
+ * slot of each group of ns rows. */
+int pn2_bn_bwd_stats(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_pm,
                      const int* argmax, int ns, int npoint, const float* y, const float* scale,
                      const float* shift, const float* mean, const float* invstd, double* s1, double* s2,
                      void* stream);
@@ -307,7 +309,7 @@ int pn2_bn_bwd_stats(long long rows, int c, int ld_da, int ld_y, const float* da
 /* dy = gamma * invstd * (dYhat - (s1 + xhat * s2) / count)  (count > 0: batch statistics) or
  * gamma * invstd * dYhat  (count == 0: frozen statistics) -> operand rows in the `terms` layout of
  * pn2_bn_relu_rows: (rows, c), (rows, 3c) or (rows, 6c) bf16. */
-int pn2_bn_bwd_rows(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_cm,
+int pn2_bn_bwd_rows(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_pm,
                     const int* argmax, int ns, int npoint, const float* y, const float* scale,
                     const float* shift, const float* mean, const float* invstd, const float* gamma,
                     const double* s1, const double* s2, long long count, int terms, void* dy_bf16,
