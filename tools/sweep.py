@@ -19,7 +19,7 @@ def run(n, npoint, b, c_in, depth):
     # one generated scene per distinct seed, tiled to the batch (generation dominates otherwise)
     base = syn.make_batch(0, min(b, 4), n, c_in)
     pcs = [torch.cat([base] * (b // base.shape[0]), 0).roll(s, 0).contiguous().to(dev) for s in range(2)]
-    throughput = depth >= 4 and 16384 <= n <= 50176
+    throughput = depth >= 4 and 16384 <= n <= 131072
     graphs = [pkg.GraphedBackbone(bb, pcs[0], throughput=throughput) for _ in range(depth)]
     streams = [torch.cuda.Stream() for _ in range(depth)]
     steps = 24 if n <= 50000 else 12
