@@ -102,3 +102,61 @@ def test_huber_loss_matches_formula(pkg):
     a = e.abs()
     want = torch.where(a <= 0.7, 0.5 * a ** 2, 0.5 * 0.7 ** 2 + 0.7 * (a - 0.7))
     torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-7)
+
+
+def test_options_are_process_wide_with_a_per_thread_override(pkg):
+    """pn2_set_option / pn2_set_option_thread (include/pointnet2_b200.h): a thread that captures a CUDA graph
+    under other settings must not change what other host threads launch."""
+    import threading
+    assert pkg.get_option("fps_bucket") == 0 and pkg.get_option("no_such_option") == -1
+    seen = {}
+
+    def other_thread():
+        seen["before"] = pkg.get_option("fps_bucket")
+        pkg.set_option_thread("fps_bucket", 1)          # override of THIS thread only
+        seen["own"] = pkg.get_option("fps_bucket")
+
+    with pkg.thread_options(fps_bucket=1, sa_tiles_per_group=16):
+        assert pkg.get_option("fps_bucket") == 1 and pkg.get_option("sa_tiles_per_group") == 16
+        t = threading.Thread(target=lambda: seen.setdefault("concurrent", pkg.get_option("fps_bucket")))
+        t.start(); t.join()
+    assert seen["concurrent"] == 0                        # the other thread saw the process-wide value
+    assert pkg.get_option("fps_bucket") == 0 and pkg.get_option("sa_tiles_per_group") == 0
+    t = threading.Thread(target=other_thread)
+    t.start(); t.join()
+    assert seen == {"concurrent": 0, "before": 0, "own": 1} and pkg.get_option("fps_bucket") == 0
+    pkg.set_option("bq_grid", 0)
+    try:
+        assert pkg.get_option("bq_grid") == 0
+    finally:
+        pkg.set_option("bq_grid", 1)
+    with pytest.raises(pkg._lib.Pn2Error):
+        pkg.set_option("no_such_option", 1)
+    with pytest.raises(pkg._lib.Pn2Error):
+        pkg.set_option_thread("no_such_option", 1)
+
+
+def test_launch_statistics_are_exposed(pkg):
+    for name in ("fps_cluster_launches", "fps_bucket_launches", "bq_grid_launches", "bq_small_grid_launches",
+                 "bq_scan_launches", "nn_small_launches", "nn_tiled_launches"):
+        assert pkg.get_stat(name) >= 0
+    with pytest.raises(pkg._lib.Pn2Error):
+        pkg.get_stat("no_such_statistic")
+
+
+def test_training_path_selection_is_host_logic(pkg):
+    """mlp_train.supported: which SharedMLPs the tcgen05 training path takes (CUDA fp32 input, conv1x1 without
+    bias + BatchNorm + ReLU blocks, widths multiples of 64 up to 256); CPU tensors and other shapes fall to
+    torch's layers, and the backend / precision switches are context managers."""
+    MT = pkg.mlp_train
+    ok = pkg.pytorch_utils.SharedMLP([8, 64, 128], bn=True)
+    assert not MT.supported(ok, torch.rand(2, 8, 5, 4))                  # CPU tensor
+    assert MT._PRECISION[0] == "bf16x6" and MT._BACKEND[0] == "tcgen05"
+    with MT.precision("bf16"), MT.mlp_backend("torch"):
+        assert MT._PRECISION[0] == "bf16" and MT._BACKEND[0] == "torch"
+    assert MT._PRECISION[0] == "bf16x6" and MT._BACKEND[0] == "tcgen05"
+    w = MT._W_BLOCKS
+    r = MT._ROW_BLOCKS
+    # the K-block pairing evaluates exactly the leading term products
+    assert sorted(zip(r[2], w[2])) == [(0, 0), (0, 1), (1, 0)]
+    assert sorted(zip(r[3], w[3])) == [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (2, 0)]
