@@ -214,8 +214,20 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   };
   long long tile = s_next[grp][0], next_tile = n_tiles;
   fetch_row(tile, 0);
+#ifdef PN2_SA_TIMING
+  long long dbg_t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, dbg_prev = clock64(), dbg_start = dbg_prev;
+  int dbg_tiles = 0, dbg_nld = 0;
+  long long dbg_ld = 0;
+#define SA_T(i) { const long long _t = clock64(); dbg_t[i] += _t - dbg_prev; dbg_prev = _t; }
+#else
+#define SA_T(i)
+#endif
 
   for (int it = 0; tile < n_tiles && !failed; ++it, tile = next_tile) {
+    SA_T(0)
+#ifdef PN2_SA_TIMING
+    ++dbg_tiles;
+#endif
     const int scene = in_scene;  // of THIS tile (fetch_row for the next one overwrites these)
     const int* rs_tile = in_rs;
     // claim the tile after this one; the group reads it after the next group_sync (the other parity
@@ -259,11 +271,13 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
       }
       fence_proxy_async_smem();
       tc::fence_before_sync();
+      SA_T(1)
       group_sync();
       if (!weights_ready) {
         if (!mbar_wait(&bar_w, 0)) { failed = true; break; }
         weights_ready = true;
       }
+      SA_T(2)
       if (tid == 0) {
         tc::fence_after_sync();
 #pragma unroll
@@ -275,6 +289,7 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
       if (!mbar_wait(&bar_mma, phase)) { failed = true; break; }
       phase ^= 1;
       tc::fence_after_sync();
+      SA_T(3)
       // epilogue 1: thread = row; ReLU folded into the bf16 conversion; X1 overwrites the operand rows
       const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
 #pragma unroll
@@ -353,11 +368,13 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     }
     fence_proxy_async_smem();
     tc::fence_before_sync();
+    SA_T(4)
     group_sync();
     if (!weights_ready) {
       if (!mbar_wait(&bar_w, 0)) { failed = true; break; }
       weights_ready = true;
     }
+    SA_T(5)
     // ---------------- layer 2: D2 = X1 . W2^T --------------------------------------------------
     if (tid == 0) {
       tc::fence_after_sync();
@@ -372,6 +389,7 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     if (!mbar_wait(&bar_mma, phase)) { failed = true; break; }
     phase ^= 1;
     tc::fence_after_sync();
+    SA_T(6)
     // ---------------- epilogue 2: thread = row; bias + ReLU -> bf16 X2 over X1 ----------------
     {
       const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
@@ -394,7 +412,9 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     }
     fence_proxy_async_smem();
     tc::fence_before_sync();
+    SA_T(7)
     group_sync();
+    SA_T(8)
     // ---------------- layer 3 (transposed), one 128-channel half at a time ----------------------
     // D3[h] = W3[h*128 .. +128] . X2^T always lands in the group's first 128 TMEM columns (aliasing D2),
     // so a group needs 128 columns whatever C3 is and up to four groups share an SM.
@@ -421,9 +441,11 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
       int cid[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) cid[q] = __ldg(rs_tile + lane + 32 * q);
+      SA_T(9)
       if (!mbar_wait(&bar_mma, phase)) { failed = true; break; }
       phase ^= 1;
       tc::fence_after_sync();
+      SA_T(10)
       // ---- epilogue 3: thread = channel; running max over the columns, flushed where a centre ends ----
       const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
       // The rows of a centre are consecutive TMEM columns; the end mask is the same for every thread, so
@@ -443,7 +465,13 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
       float mx = -INFINITY;
       for (int c0 = 0; c0 <= last_col; c0 += 16) {
         float v[16];
+#ifdef PN2_SA_TIMING
+        const long long _l0 = clock64();
+#endif
         tc::tmem_ld16(lane_base + c0, v);
+#ifdef PN2_SA_TIMING
+        dbg_ld += clock64() - _l0; ++dbg_nld;
+#endif
         const uint32_t bits = (endm[c0 >> 5] >> (c0 & 31)) & 0xffffu;
         const int cidq = (c0 & 64) ? ((c0 & 32) ? cid[3] : cid[2]) : ((c0 & 32) ? cid[1] : cid[0]);
         // four columns at a time: where no centre ends inside them (the common case: 28 / 7 / 14 rows per
@@ -469,7 +497,18 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     }
     if (failed) break;
     tc::fence_before_sync();  // ordered before the next tile's __syncthreads / MMA into the same TMEM
+    SA_T(11)
   }
+#ifdef PN2_SA_TIMING
+  if (tid == 0 && grp == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && dbg_tiles > 0)
+    printf("sa_fused[cta %d of %d, C1 %d C2 %d C3 %d MMA1 %d NG %d]: %d tiles, %lld cycles/tile; prologue %lld; per tile: "
+           "loop-top %lld build %lld sync1 %lld mma1 %lld epi1 %lld sync2 %lld mma2 %lld epi2 %lld sync3 %lld "
+           "issue3+prefetch %lld mma3-wait %lld epi3 %lld (of which %d tmem loads: %lld)\n",
+           blockIdx.x, gridDim.x, C1, C2, C3, int(MMA1), NG, dbg_tiles, (clock64() - dbg_start) / dbg_tiles, dbg_start,
+           dbg_t[0] / dbg_tiles, dbg_t[1] / dbg_tiles, dbg_t[2] / dbg_tiles, dbg_t[3] / dbg_tiles, dbg_t[4] / dbg_tiles,
+           dbg_t[5] / dbg_tiles, dbg_t[6] / dbg_tiles, dbg_t[7] / dbg_tiles, dbg_t[8] / dbg_tiles, dbg_t[9] / dbg_tiles,
+           dbg_t[10] / dbg_tiles, dbg_t[11] / dbg_tiles, dbg_nld / dbg_tiles, dbg_ld / dbg_tiles);
+#endif
   if (failed && tid == 0) atomicExch(a.err, 2);
   // a group that found no tile never waited for the weights: the bulk copies must have landed before
   // this CTA's shared memory can be handed to another CTA
@@ -618,8 +657,8 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
   PN2_REQUIRE(radius_div != 0.f, "sa_group_mlp: radius_div must be non-zero");
   SaArgs a;
   a.xyz = xyz; a.new_xyz = new_xyz; a.idx = idx; a.g = g; a.feat = feat; a.w1 = w1; a.b1 = b1;
-  a.w2p = static_cast<const uint8_t*>(w2_packed); a.b2 = b2; a.w3p = static_cast<const uint8_t*>(w3_packed); a.b3 = b3;
   a.out_cm = out_cm;
+  a.w2p = static_cast<const uint8_t*>(w2_packed); a.b2 = b2; a.w3p = static_cast<const uint8_t*>(w3_packed); a.b3 = b3;
   a.B = b; a.N = n; a.npoint = npoint; a.ns = nsample; a.C1 = c1; a.C2 = c2; a.C3 = c3;
   a.radius_div = radius_div;
   a.ns_shift = nsample == 16 ? 4 : (nsample == 32 ? 5 : (nsample == 64 ? 6 : 7));
