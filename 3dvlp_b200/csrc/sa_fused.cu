@@ -173,47 +173,66 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   bool weights_ready = false, failed = false;
 
   // Inputs of this thread's row: compacted row -> (centre, slot) -> neighbour index -> point coordinates,
-  // centre, raw channels.  A dependent chain of global round trips, so the NEXT tile's inputs are
-  // requested while the current tile is still in its layer-3 epilogue.
+  // centre, raw channels: a dependent chain of global round trips, requested for the NEXT tile while the
+  // current one is being processed.
   float in_p[3], in_c[3], in_f[CD > 0 ? CD : 1];
   long long in_grow = 0;
   bool in_ok = false;
   int in_scene = 0;
   const int* in_rs = a.row_src;  // compacted rows of the tile
-  auto fetch_row = [&](long long t, int par) {
+  // The chain is requested in three stages, each consumed a phase after it was issued, so that none of its two
+  // dependent global round trips is ever waited for on the spot:
+  //   A (after the tile's first group_sync)  compacted-row entries of the NEXT tile: row_src[tid], row_src[tid + 1]
+  //   B (before the layer-3 group_sync)      -> centre id, end-of-centre mask; requests idx[src] and the centre
+  //   C (after the layer-3 MMA is issued)    -> point id; requests the point's coordinates / raw channels
+  int nx_src = -1, nx_nxt = -1, nx_pi = 0, nx_jg = -1;
+  bool nx_valid = false;
+  auto fetch_a = [&](long long t) {
+    nx_valid = t < n_tiles;  // uniform over the group
+    nx_src = nx_nxt = -1;
+    if (!nx_valid) return;
+    int b = 0;
+    while (s_tpre[b + 1] <= t) ++b;  // scene of the tile (few scenes: linear search)
+    in_scene = b;
+    const int* rs = a.row_src + static_cast<long long>(b) * a.cap + (t - s_tpre[b]) * 128;
+    in_rs = rs;
+    nx_src = __ldg(rs + tid);
+    nx_nxt = tid < 127 ? __ldg(rs + tid + 1) : -1;
+  };
+  auto fetch_b = [&](int par) {
     in_ok = false;
     in_grow = 0;
 #pragma unroll
     for (int d = 0; d < 3; ++d) in_p[d] = in_c[d] = 0.f;
 #pragma unroll
     for (int d = 0; d < (CD > 0 ? CD : 1); ++d) in_f[d] = 0.f;
-    if (t >= n_tiles) return;  // uniform over the group
-    int b = 0;
-    while (s_tpre[b + 1] <= t) ++b;  // scene of the tile (few scenes: linear search)
-    in_scene = b;
-    const int* rs = a.row_src + static_cast<long long>(b) * a.cap + (t - s_tpre[b]) * 128;
-    in_rs = rs;
-    const int src = __ldg(rs + tid);
-    const int nxt = tid < 127 ? __ldg(rs + tid + 1) : -1;
-    const int jg = src >= 0 ? (src >> a.ns_shift) : -1;  // global centre index b*npoint + j (< 2^31, host-checked)
+    if (!nx_valid) return;
+    const int src = nx_src;
+    nx_jg = src >= 0 ? (src >> a.ns_shift) : -1;  // global centre index b*npoint + j (< 2^31, host-checked)
     // a centre may continue in the next tile: each tile flushes its part with an atomic max
-    const bool last = src >= 0 && (nxt < 0 || (nxt >> a.ns_shift) != jg);
+    const bool last = src >= 0 && (nx_nxt < 0 || (nx_nxt >> a.ns_shift) != nx_jg);
     const uint32_t m = __ballot_sync(0xffffffffu, last);
     if (lane == 0) s_end[grp][par][warp] = m;
     in_ok = src >= 0;
     if (in_ok) {
-      const int pi = __ldg(a.idx + src);
-      in_grow = static_cast<long long>(b) * a.N + pi;  // row of g / point id within the batch-flattened cloud
-      const float* p = a.xyz + in_grow * 3;
-      const float* c = a.new_xyz + static_cast<long long>(jg) * 3;
+      nx_pi = __ldg(a.idx + src);
+      const float* c = a.new_xyz + static_cast<long long>(nx_jg) * 3;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) { in_p[d] = __ldg(p + d); in_c[d] = __ldg(c + d); }
-#pragma unroll
-      for (int d = 0; d < CD; ++d) in_f[d] = __ldg(a.feat + (static_cast<size_t>(b) * CD + d) * a.N + pi);
+      for (int d = 0; d < 3; ++d) in_c[d] = __ldg(c + d);
     }
   };
+  auto fetch_c = [&]() {
+    if (!nx_valid || !in_ok) return;
+    const int pi = nx_pi;
+    in_grow = static_cast<long long>(in_scene) * a.N + pi;  // row of g / point id within the batch-flattened cloud
+    const float* p = a.xyz + in_grow * 3;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) in_p[d] = __ldg(p + d);
+#pragma unroll
+    for (int d = 0; d < CD; ++d) in_f[d] = __ldg(a.feat + (static_cast<size_t>(in_scene) * CD + d) * a.N + pi);
+  };
   long long tile = s_next[grp][0], next_tile = n_tiles;
-  fetch_row(tile, 0);
+  fetch_a(tile); fetch_b(0); fetch_c();  // the first tile's inputs: requested back to back
 #ifdef PN2_SA_TIMING
   long long dbg_t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, dbg_prev = clock64(), dbg_start = dbg_prev;
   int dbg_tiles = 0, dbg_nld = 0;
@@ -277,6 +296,8 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
         if (!mbar_wait(&bar_w, 0)) { failed = true; break; }
         weights_ready = true;
       }
+      next_tile = s_next[grp][(it + 1) & 1];  // claimed by thread 0 before the group_sync above
+      fetch_a(next_tile);
       SA_T(2)
       if (tid == 0) {
         tc::fence_after_sync();
@@ -374,6 +395,10 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
       if (!mbar_wait(&bar_w, 0)) { failed = true; break; }
       weights_ready = true;
     }
+    if (!MMA1) {  // this is the tile's first group_sync in gather mode
+      next_tile = s_next[grp][(it + 1) & 1];
+      fetch_a(next_tile);
+    }
     SA_T(5)
     // ---------------- layer 2: D2 = X1 . W2^T --------------------------------------------------
     if (tid == 0) {
@@ -410,6 +435,7 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
                      : "memory");
       }
     }
+    fetch_b((it + 1) & 1);  // next tile: centre ids / end mask from the row entries, request idx and the centre
     fence_proxy_async_smem();
     tc::fence_before_sync();
     SA_T(7)
@@ -433,10 +459,7 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
         }
         tc::mma_commit(&bar_mma);
       }
-      if (h == 0) {  // next tile's inputs travel under this tile's epilogue
-        next_tile = s_next[grp][(it + 1) & 1];
-        fetch_row(next_tile, (it + 1) & 1);
-      }
+      if (h == 0) fetch_c();  // next tile: the points' coordinates / raw channels travel under this tile's epilogue
       // centre of column lane + 32 q (warp-uniform at flush time: fetched by shuffle), requested before the wait
       int cid[4];
 #pragma unroll
