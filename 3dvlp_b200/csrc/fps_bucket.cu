@@ -74,8 +74,11 @@ __device__ __forceinline__ int warp_argmax2(int& v, uint32_t& k) {
   return __ffs(win) - 1;
 }
 
+#ifndef PN2_FB_MAXREG
+#define PN2_FB_MAXREG 64
+#endif
 template <int PPL, bool GT>
-__global__ void __launch_bounds__(FB_THREADS, 1) fps_bucket_kernel(const FbArgs a) {
+__global__ void __maxnreg__(PN2_FB_MAXREG) fps_bucket_kernel(const FbArgs a) {
   constexpr int FB_BK = 32 * PPL;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ float4 ctr[FB_KMAX];     // accepted centres (x, y, z, key bits)
