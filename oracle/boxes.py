@@ -4,12 +4,14 @@ INFRASTRUCTURE ONLY (see oracle/oracle.py for who may import this).
 * ``box3d_diou_batch_tensor`` restates /root/reference/utils/box_util.py:488-528 op for op; it is pinned
   against the reference function itself by tests/golden/reference_boxes.npz
   (tests/golden/make_golden_boxes.py imports the reference in the build container).
-* ``compute_diou_loss_loop`` restates lib/loss_helper/loss_grounding.py:129-365 with its Python loops
-  (the reference module cannot be imported here: it needs torch_scatter and easydict) --
-  "parity unpinned" beyond its building blocks (box3d_diou_batch_tensor, SoftmaxRankingLoss), which are.
-* ``contrast_loop`` restates models/constrast_module/constrast_module.py:52-131 with its loops;
-  pytorch3d's ``box3d_overlap`` (not vendored, not installed, version unpinned by the reference) is
-  replaced by the closed-form IoU of the axis-aligned boxes it is called on -- "parity unpinned".
+* ``compute_diou_loss_loop`` restates lib/loss_helper/loss_grounding.py:129-365 with its Python loops; since
+  round 2 it is pinned against the reference function itself (imported with stand-ins for torch_scatter /
+  easydict by tests/golden/make_golden_losses.py): tests/test_losses_golden.py replays
+  tests/golden/reference_losses.npz through it in the CPU suite.
+* ``contrast_loop`` restates models/constrast_module/constrast_module.py:52-131 with its loops; pinned the same
+  way against the reference's own ContrastModule.  pytorch3d's ``box3d_overlap`` (not vendored, not installed,
+  version unpinned by the reference) is replaced -- here and in the generator's stand-in -- by the closed-form
+  IoU of the axis-aligned boxes it is called on: that one third-party call stays "parity unpinned".
 """
 import torch
 import torch.nn.functional as F
