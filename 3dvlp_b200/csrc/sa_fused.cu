@@ -36,7 +36,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 }
 
 constexpr int SA_THREADS = 128;
-constexpr int kMaxScenes = 64;  // scenes per launch
+constexpr int kMaxScenes = 64;  // scenes per launch (the tile prefix scan holds two per lane of one warp)
 
 struct SaArgs {
   const float* xyz;      // (B, N, 3)
@@ -84,6 +84,13 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   __shared__ int s_tpre[kMaxScenes + 1];  // prefix sums of tiles_b: tile id -> scene
   __shared__ float s_b2[128];
 
+#ifdef PN2_SA_TIMING
+  const long long dbg_entry = clock64();
+  long long dbg_p[5] = {0, 0, 0, 0, 0};
+#define SA_P(i) dbg_p[i] = clock64() - dbg_entry;
+  unsigned long long dbg_g0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
+#endif
   constexpr int C1 = 32 * CPL;
   const int grp = threadIdx.x / SA_THREADS;            // group of this thread
   const int tid = threadIdx.x % SA_THREADS, lane = tid & 31, warp = tid >> 5;  // within the group
@@ -109,41 +116,83 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   if (MMA1) {
     // B operand of layer 1: row = channel, K-major: [w_h, w_h, w_m, w_h, w_l, w_m] per input (against
     // [v_h, v_m, v_h, v_l, v_h, v_m]), [b_h, b_m, b_l] against ones, zeros up to K0
-    for (int e = threadIdx.x; e < C1 * K0; e += SA_THREADS * NG) {
+    // the weights of a batch of WB elements are requested before the first is converted: the loop costs one or
+    // two global round trips per CTA instead of one per element (16 -- 13 k cycles, more than a tile -- in SA1)
+    constexpr int WB = 16;
+    auto w1_term = [&](int e, int& part) -> const float* {  // element e of the panel: which weight, which split term
       const int ch = e / K0, k = e - ch * K0;
-      float w = 0.f;
-      int part = 0;  // 0 = h, 1 = m, 2 = l
+      part = 0;  // 0 = h, 1 = m, 2 = l
       if (k < NT - 3) {
-        w = a.w1[static_cast<size_t>(ch) * (3 + CD) + k / 6];
         const int t = k % 6;
         part = t == 2 || t == 5 ? 1 : (t == 4 ? 2 : 0);
-      } else if (k < NT) {
-        w = a.b1[ch];
-        part = k - (NT - 3);
+        return a.w1 + static_cast<size_t>(ch) * (3 + CD) + k / 6;
       }
-      const __nv_bfloat16 h = __float2bfloat16_rn(w);
-      const float r1 = w - __bfloat162float(h);
-      const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-      const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
-      const __nv_bfloat16 val = part == 0 ? h : (part == 1 ? m : l);
-      const uint32_t addr = s_w1 + tc::swz_off(ch, static_cast<uint32_t>(k) >> 3) + (k & 7) * 2;
-      asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__bfloat16_as_ushort(val)) : "memory");
+      if (k < NT) { part = k - (NT - 3); return a.b1 + ch; }
+      return nullptr;  // zero padding up to K0
+    };
+    for (int e0 = threadIdx.x; e0 < C1 * K0; e0 += SA_THREADS * NG * WB) {
+      float wv[WB];
+#pragma unroll
+      for (int u = 0; u < WB; ++u) {
+        const int e = e0 + u * SA_THREADS * NG;
+        int part;
+        const float* src = e < C1 * K0 ? w1_term(e, part) : nullptr;
+        wv[u] = src ? __ldg(src) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < WB; ++u) {
+        const int e = e0 + u * SA_THREADS * NG;
+        if (e >= C1 * K0) break;
+        int part;
+        w1_term(e, part);
+        const float w = wv[u];
+        const __nv_bfloat16 h = __float2bfloat16_rn(w);
+        const float r1 = w - __bfloat162float(h);
+        const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+        const __nv_bfloat16 val = part == 0 ? h : (part == 1 ? m : l);
+        const int ch = e / K0, k = e - ch * K0;
+        const uint32_t addr = s_w1 + tc::swz_off(ch, static_cast<uint32_t>(k) >> 3) + (k & 7) * 2;
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(__bfloat16_as_ushort(val)) : "memory");
+      }
     }
     fence_proxy_async_smem();
   }
+#ifdef PN2_SA_TIMING
+  SA_P(0)
+#endif
   // Tiles come from a global counter, not from a static stride: when other kernels hold some SMs
   // (several batches in flight) part of the grid starts late, and a late CTA must find the work
   // already done instead of a full static share of it.
-  if (tid == 0) s_next[grp][0] = atomicAdd(a.tile_counter, 1);
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int b = 0; b < a.B; ++b) { s_tpre[b] = acc; acc += __ldg(a.tiles_b + b); }
-    s_tpre[a.B] = acc;
+  // the first tile of a group is static (no round trip before the first gather); the rest come from the counter
+  if (tid == 0) s_next[grp][0] = blockIdx.x * NG + grp;
+  if (threadIdx.x < 32) {
+    // prefix sums of the scenes' tile counts by one warp: a single global round trip (kMaxScenes = 64 = 2 per lane)
+    const int l = threadIdx.x;
+    int i0 = l < a.B ? __ldg(a.tiles_b + l) : 0, i1 = l + 32 < a.B ? __ldg(a.tiles_b + l + 32) : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o0 = __shfl_up_sync(0xffffffffu, i0, d), o1 = __shfl_up_sync(0xffffffffu, i1, d);
+      if (l >= d) { i0 += o0; i1 += o1; }
+    }
+    i1 += __shfl_sync(0xffffffffu, i0, 31);
+    if (l == 0) s_tpre[0] = 0;
+    if (l < a.B) s_tpre[l + 1] = i0;
+    if (l + 32 < a.B) s_tpre[l + 33] = i1;
+#ifdef PN2_SA_TIMING
+    SA_P(1)
+#endif
+    tc::tmem_alloc(&tmem_slot, tmem_cols);
+#ifdef PN2_SA_TIMING
+    SA_P(2)
+#endif
   }
-  if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot, tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+#ifdef PN2_SA_TIMING
+  SA_P(3)
+#endif
   const uint32_t tmem_base = tmem_slot;
   const uint32_t tmem_d = tmem_base + grp * group_cols;
   auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(SA_THREADS) : "memory"); };
@@ -191,7 +240,7 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     nx_valid = t < n_tiles;  // uniform over the group
     nx_src = nx_nxt = -1;
     if (!nx_valid) return;
-    int b = 0;
+    int b = in_scene;                // a group's tiles only grow: search on from the current scene
     while (s_tpre[b + 1] <= t) ++b;  // scene of the tile (few scenes: linear search)
     in_scene = b;
     const int* rs = a.row_src + static_cast<long long>(b) * a.cap + (t - s_tpre[b]) * 128;
@@ -234,6 +283,9 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   long long tile = s_next[grp][0], next_tile = n_tiles;
   fetch_a(tile); fetch_b(0); fetch_c();  // the first tile's inputs: requested back to back
 #ifdef PN2_SA_TIMING
+  SA_P(4)
+#endif
+#ifdef PN2_SA_TIMING
   long long dbg_t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, dbg_prev = clock64(), dbg_start = dbg_prev;
   int dbg_tiles = 0, dbg_nld = 0;
   long long dbg_ld = 0;
@@ -249,9 +301,14 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
 #endif
     const int scene = in_scene;  // of THIS tile (fetch_row for the next one overwrites these)
     const int* rs_tile = in_rs;
+    // centre of column lane + 32 q (warp-uniform at flush time: fetched by shuffle), requested a whole tile before
+    // the layer-3 epilogue needs it
+    int cid[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cid[q] = __ldg(rs_tile + lane + 32 * q);
     // claim the tile after this one; the group reads it after the next group_sync (the other parity
     // slot was last read an iteration ago, several group_syncs back)
-    if (tid == 0) s_next[grp][(it + 1) & 1] = atomicAdd(a.tile_counter, 1);
+    if (tid == 0) s_next[grp][(it + 1) & 1] = static_cast<int>(gridDim.x) * NG + atomicAdd(a.tile_counter, 1);
     // pointnet2_utils.py:345-348: grouped_xyz -= new_xyz; grouped_xyz /= radius  (fp32 divide)
     const bool ok = in_ok;
     const long long grow = in_grow;
@@ -411,6 +468,9 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
       }
       tc::mma_commit(&bar_mma);
     }
+    // next tile: centre ids / end mask from the row entries (requested a phase ago), request idx and the centre --
+    // here, not after the epilogue, so that idx has the whole epilogue to arrive before fetch_c needs it
+    fetch_b((it + 1) & 1);
     if (!mbar_wait(&bar_mma, phase)) { failed = true; break; }
     phase ^= 1;
     tc::fence_after_sync();
@@ -435,7 +495,6 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
                      : "memory");
       }
     }
-    fetch_b((it + 1) & 1);  // next tile: centre ids / end mask from the row entries, request idx and the centre
     fence_proxy_async_smem();
     tc::fence_before_sync();
     SA_T(7)
@@ -460,10 +519,6 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
         tc::mma_commit(&bar_mma);
       }
       if (h == 0) fetch_c();  // next tile: the points' coordinates / raw channels travel under this tile's epilogue
-      // centre of column lane + 32 q (warp-uniform at flush time: fetched by shuffle), requested before the wait
-      int cid[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) cid[q] = __ldg(rs_tile + lane + 32 * q);
       SA_T(9)
       if (!mbar_wait(&bar_mma, phase)) { failed = true; break; }
       phase ^= 1;
@@ -486,16 +541,32 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
       int* out_bits = reinterpret_cast<int*>(a.out_cm) + (static_cast<long long>(scene) * C3 + ch) * a.npoint -
                       static_cast<long long>(scene) * a.npoint;  // + global centre index
       float mx = -INFINITY;
+      // NOT unrolled: the body (a fast path and a per-column path for each of four column quads) is ~4 KB of
+      // code; eight copies made the tile loop larger than the 32 KB instruction cache the SM's four groups
+      // share, and every skipped slow path was an instruction-fetch miss
+#pragma unroll 1
       for (int c0 = 0; c0 <= last_col; c0 += 16) {
         float v[16];
 #ifdef PN2_SA_TIMING
         const long long _l0 = clock64();
 #endif
+#ifdef PN2_SA_EXP_NOLD
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __int_as_float(c0 + i + tid + it);
+#else
         tc::tmem_ld16(lane_base + c0, v);
+#endif
 #ifdef PN2_SA_TIMING
         dbg_ld += clock64() - _l0; ++dbg_nld;
 #endif
-        const uint32_t bits = (endm[c0 >> 5] >> (c0 & 31)) & 0xffffu;
+#ifdef PN2_SA_EXP_NOMAX
+        mx = fmaxf(mx, v[0] + v[15]);
+        if (c0 == 112) asm volatile("red.global.max.s32 [%0], %1;" ::"l"(out_bits + (cid[0] >> a.ns_shift)), "r"(__float_as_int(fmaxf(mx + bias, 0.f))) : "memory");
+        continue;
+#endif
+        // (selects, not endm[c0 >> 5]: a dynamically indexed array would live in local memory)
+        const uint32_t e_lo = (c0 & 64) ? endm[2] : endm[0], e_hi = (c0 & 64) ? endm[3] : endm[1];
+        const uint32_t bits = (((c0 & 32) ? e_hi : e_lo) >> (c0 & 31)) & 0xffffu;
         const int cidq = (c0 & 64) ? ((c0 & 32) ? cid[3] : cid[2]) : ((c0 & 32) ? cid[1] : cid[0]);
         // four columns at a time: where no centre ends inside them (the common case: 28 / 7 / 14 rows per
         // centre in SA1 / SA2 / SA3-4) the running max is two 3-input FMNMX3 and one warp-uniform test
@@ -510,6 +581,9 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
               mx = fmaxf(mx, v[i]);
               if (bits & (1u << i)) {
                 const int jg = __shfl_sync(0xffffffffu, cidq, (c0 + i) & 31) >> a.ns_shift;
+#ifdef PN2_SA_EXP_NORED  // experiment: how much of the epilogue is the throughput of the scattered reductions
+                if (__float_as_int(fmaxf(mx + bias, 0.f)) == 0x7fc12345)
+#endif
                 asm volatile("red.global.max.s32 [%0], %1;" ::"l"(out_bits + jg), "r"(__float_as_int(fmaxf(mx + bias, 0.f))) : "memory");
                 mx = -INFINITY;
               }
@@ -523,11 +597,14 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     SA_T(11)
   }
 #ifdef PN2_SA_TIMING
-  if (tid == 0 && grp == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && dbg_tiles > 0)
-    printf("sa_fused[cta %d of %d, C1 %d C2 %d C3 %d MMA1 %d NG %d]: %d tiles, %lld cycles/tile; prologue %lld; per tile: "
+  unsigned long long dbg_g1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g1));
+  if (tid == 0 && grp == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1) && dbg_tiles > 0)
+    printf("sa_fused[cta %d of %d, C1 %d C2 %d C3 %d MMA1 %d NG %d]: globaltimer entry %llu ns, lifetime %llu ns; %d tiles, %lld cycles/tile; prologue %lld cycles (w1 panel %lld, tile prefix %lld, tmem alloc %lld, sync %lld, first fetch chain %lld); per tile: "
            "loop-top %lld build %lld sync1 %lld mma1 %lld epi1 %lld sync2 %lld mma2 %lld epi2 %lld sync3 %lld "
            "issue3+prefetch %lld mma3-wait %lld epi3 %lld (of which %d tmem loads: %lld)\n",
-           blockIdx.x, gridDim.x, C1, C2, C3, int(MMA1), NG, dbg_tiles, (clock64() - dbg_start) / dbg_tiles, dbg_start,
+           blockIdx.x, gridDim.x, C1, C2, C3, int(MMA1), NG, dbg_g0 % 100000000ull, dbg_g1 - dbg_g0, dbg_tiles,
+           (clock64() - dbg_start) / dbg_tiles, dbg_start - dbg_entry, dbg_p[0], dbg_p[1], dbg_p[2], dbg_p[3], dbg_p[4],
            dbg_t[0] / dbg_tiles, dbg_t[1] / dbg_tiles, dbg_t[2] / dbg_tiles, dbg_t[3] / dbg_tiles, dbg_t[4] / dbg_tiles,
            dbg_t[5] / dbg_tiles, dbg_t[6] / dbg_tiles, dbg_t[7] / dbg_tiles, dbg_t[8] / dbg_tiles, dbg_t[9] / dbg_tiles,
            dbg_t[10] / dbg_tiles, dbg_t[11] / dbg_tiles, dbg_nld / dbg_tiles, dbg_ld / dbg_tiles);
@@ -719,13 +796,15 @@ extern "C" int pn2_sa_group_mlp(int b, int n, int npoint, int nsample, float rad
   const size_t x_bytes = 128 * static_cast<size_t>(c1 > c2 ? c1 : c2) * 2;
   const long long tiles = (a.total_rows + 127) / 128;
   // Groups per CTA: as many independent 128-thread groups (own tile, own 128 TMEM columns) as shared
-  // memory allows, up to 4 (4 x 128 = all 512 TMEM columns).  Small weight sets that would fit several
-  // CTAs per SM anyway keep one group per CTA.
+  // memory allows, up to 4 (4 x 128 = all 512 TMEM columns), in ONE CTA per SM: the per-CTA prologue
+  // (layer-1 operand panel, weight TMA, TMEM allocation: ~13 k cycles, more than a tile) is then paid once
+  // per SM instead of once per group (SA1: +5 % on the whole step against four single-group CTAs per SM).
+  // Only calls too small to give every SM four tiles keep single-group CTAs, spread over more SMs.
   const size_t limit = 227 * 1024 - 2048;  // leave room for the static shared memory
   const size_t smem1 = w_bytes + x_bytes + 1024;
   int ng = 1, resident = 1;
-  if (smem1 <= 56 * 1024) {
-    resident = 4;  // four single-group CTAs per SM (SA1-sized weights)
+  if (smem1 <= 56 * 1024 && tiles < 4LL * sm_count()) {
+    resident = 4;  // four single-group CTAs per SM (SA1-sized weights, small call)
   } else {
     ng = 4;
     while (ng > 1 && w_bytes + ng * x_bytes + 1024 > limit) ng >>= 1;

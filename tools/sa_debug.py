@@ -3,13 +3,14 @@ fused SA launch) into tools/_build and run one backbone forward.  Usage: python 
 import importlib, os, subprocess, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "3dvlp_b200", "csrc")
-OUT = os.path.join(ROOT, "tools", "_build", "libsa_debug.so")
+EXP = os.environ.get("PN2_SA_EXP", "")  # e.g. NOLD / NOMAX / NORED: -DPN2_SA_EXP_<name>
+OUT = os.path.join(ROOT, "tools", "_build", "libsa_debug%s.so" % EXP)
 
 
 def build():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
-    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O3", "-std=c++17", "-lineinfo", "-DPN2_SA_TIMING", "-gencode",
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O3", "-std=c++17", "-lineinfo", "-DPN2_SA_TIMING"] + (["-DPN2_SA_EXP_" + EXP] if EXP else []) + ["-gencode",
                            "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + srcs +
                           ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
 
