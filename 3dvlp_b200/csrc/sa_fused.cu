@@ -75,12 +75,13 @@ struct SaArgs {
 // exact in the fp32 accumulator and the dropped terms are ~2^-24 relative, i.e. the result matches the
 // fp32 FMA chain to fp32 rounding -- the bf16 rounding that follows sees the same values.
 template <int CPL, int CD, int NG, bool MMA1>  // C1 = 32 * CPL, raw feature channels, groups, layer 1 on MMA
-__global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs a) {
+__global__ void __maxnreg__(128) sa_fused_kernel(const SaArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, bar_mma_g[NG];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_next[NG][2];  // next tile of each group, double-buffered by iteration parity
   __shared__ uint32_t s_end[NG][2][4];    // bit r: row r of the group's tile is the last row of its centre in this tile
+  __shared__ int s_jg0[NG][2];            // global centre index of the tile's row 0
   __shared__ int s_tpre[kMaxScenes + 1];  // prefix sums of tiles_b: tile id -> scene
   __shared__ float s_b2[128];
 
@@ -228,7 +229,6 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
   long long in_grow = 0;
   bool in_ok = false;
   int in_scene = 0;
-  const int* in_rs = a.row_src;  // compacted rows of the tile
   // The chain is requested in three stages, each consumed a phase after it was issued, so that none of its two
   // dependent global round trips is ever waited for on the spot:
   //   A (after the tile's first group_sync)  compacted-row entries of the NEXT tile: row_src[tid], row_src[tid + 1]
@@ -244,7 +244,6 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     while (s_tpre[b + 1] <= t) ++b;  // scene of the tile (few scenes: linear search)
     in_scene = b;
     const int* rs = a.row_src + static_cast<long long>(b) * a.cap + (t - s_tpre[b]) * 128;
-    in_rs = rs;
     nx_src = __ldg(rs + tid);
     nx_nxt = tid < 127 ? __ldg(rs + tid + 1) : -1;
   };
@@ -262,6 +261,7 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     const bool last = src >= 0 && (nx_nxt < 0 || (nx_nxt >> a.ns_shift) != nx_jg);
     const uint32_t m = __ballot_sync(0xffffffffu, last);
     if (lane == 0) s_end[grp][par][warp] = m;
+    if (tid == 0) s_jg0[grp][par] = nx_jg;  // row 0 of a claimed tile always exists
     in_ok = src >= 0;
     if (in_ok) {
       nx_pi = __ldg(a.idx + src);
@@ -300,12 +300,6 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
     ++dbg_tiles;
 #endif
     const int scene = in_scene;  // of THIS tile (fetch_row for the next one overwrites these)
-    const int* rs_tile = in_rs;
-    // centre of column lane + 32 q (warp-uniform at flush time: fetched by shuffle), requested a whole tile before
-    // the layer-3 epilogue needs it
-    int cid[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) cid[q] = __ldg(rs_tile + lane + 32 * q);
     // claim the tile after this one; the group reads it after the next group_sync (the other parity
     // slot was last read an iteration ago, several group_syncs back)
     if (tid == 0) s_next[grp][(it + 1) & 1] = static_cast<int>(gridDim.x) * NG + atomicAdd(a.tile_counter, 1);
@@ -538,8 +532,10 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
       for (int w = 0; w < 4; ++w) endm[w] = s_end[grp][par][w];
       const int last_col = endm[3] ? 127 - __clz(endm[3]) : (endm[2] ? 95 - __clz(endm[2])
                          : (endm[1] ? 63 - __clz(endm[1]) : (endm[0] ? 31 - __clz(endm[0]) : -1)));
-      int* out_bits = reinterpret_cast<int*>(a.out_cm) + (static_cast<long long>(scene) * C3 + ch) * a.npoint -
-                      static_cast<long long>(scene) * a.npoint;  // + global centre index
+      // Every centre owns at least one compacted row and the rows of a scene are listed in centre order, so the
+      // centres that end in a tile are consecutive: the flush address is a running pointer, no lookup.
+      int* out_p = reinterpret_cast<int*>(a.out_cm) + (static_cast<long long>(scene) * C3 + ch) * a.npoint -
+                   static_cast<long long>(scene) * a.npoint + s_jg0[grp][par];
       float mx = -INFINITY;
       // NOT unrolled: the body (a fast path and a per-column path for each of four column quads) is ~4 KB of
       // code; eight copies made the tile loop larger than the 32 KB instruction cache the SM's four groups
@@ -561,13 +557,12 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
 #endif
 #ifdef PN2_SA_EXP_NOMAX
         mx = fmaxf(mx, v[0] + v[15]);
-        if (c0 == 112) asm volatile("red.global.max.s32 [%0], %1;" ::"l"(out_bits + (cid[0] >> a.ns_shift)), "r"(__float_as_int(fmaxf(mx + bias, 0.f))) : "memory");
+        if (c0 == 112) asm volatile("red.global.max.s32 [%0], %1;" ::"l"(out_p), "r"(__float_as_int(fmaxf(mx + bias, 0.f))) : "memory");
         continue;
 #endif
         // (selects, not endm[c0 >> 5]: a dynamically indexed array would live in local memory)
         const uint32_t e_lo = (c0 & 64) ? endm[2] : endm[0], e_hi = (c0 & 64) ? endm[3] : endm[1];
         const uint32_t bits = (((c0 & 32) ? e_hi : e_lo) >> (c0 & 31)) & 0xffffu;
-        const int cidq = (c0 & 64) ? ((c0 & 32) ? cid[3] : cid[2]) : ((c0 & 32) ? cid[1] : cid[0]);
         // four columns at a time: where no centre ends inside them (the common case: 28 / 7 / 14 rows per
         // centre in SA1 / SA2 / SA3-4) the running max is two 3-input FMNMX3 and one warp-uniform test
         // instead of four max + four tests; max is exact, so the grouping cannot change a bit
@@ -580,11 +575,11 @@ __global__ void __launch_bounds__(SA_THREADS * NG) sa_fused_kernel(const SaArgs 
             for (int i = 4 * q4; i < 4 * q4 + 4; ++i) {
               mx = fmaxf(mx, v[i]);
               if (bits & (1u << i)) {
-                const int jg = __shfl_sync(0xffffffffu, cidq, (c0 + i) & 31) >> a.ns_shift;
 #ifdef PN2_SA_EXP_NORED  // experiment: how much of the epilogue is the throughput of the scattered reductions
                 if (__float_as_int(fmaxf(mx + bias, 0.f)) == 0x7fc12345)
 #endif
-                asm volatile("red.global.max.s32 [%0], %1;" ::"l"(out_bits + jg), "r"(__float_as_int(fmaxf(mx + bias, 0.f))) : "memory");
+                asm volatile("red.global.max.s32 [%0], %1;" ::"l"(out_p), "r"(__float_as_int(fmaxf(mx + bias, 0.f))) : "memory");
+                ++out_p;
                 mx = -INFINITY;
               }
             }
