@@ -33,6 +33,16 @@ namespace {
 constexpr int FB_THREADS = 1024;
 constexpr int FB_WARPS = 32;
 constexpr int FB_KMAX = 16;       // centres accepted per round at most
+// Candidate groups per warp: the select step can cut a warp's buckets into FB_CPW lane segments, each reporting its
+// own candidate and bound (segmented redux.sync), for 32 * FB_CPW candidates instead of 32: the bound -- the best
+// value no group reported -- then comes from smaller groups and more samples are accepted per round.  Measured on
+// 8 x 40 000 points (tools/fb_debug.py): 418 / 348 / 300 rounds for 1 / 2 / 4, but the segmented select
+// (0.9 k -> 1.7 k -> 2.3 k cycles) and the single-warp greedy replay over more candidates (1.5 k -> 2.1 k -> 4.5 k)
+// cost more than the saved rounds: 3.9 M / 4.2 M / 4.9 M cycles per scene.  Kept at 1.
+#ifndef PN2_FB_CPW
+#define PN2_FB_CPW 1
+#endif
+constexpr int FB_CPW = PN2_FB_CPW, FB_GL = 32 / FB_CPW, FB_NC = FB_WARPS * FB_CPW;
 constexpr int FB_CELLS = 8192;    // sort grid: 32 x 32 (Morton) x 8
 // Points per bucket = 32 * PPL (PPL points per lane).  Scenes of up to 50 176 points use PPL = 2 with the running
 // minima in shared memory; larger scenes (up to 131 072 points: thread = bucket caps the buckets at 1024) use
@@ -64,16 +74,6 @@ __device__ __forceinline__ uint32_t part1by1(uint32_t v) {  // spread the low 5 
   return v;
 }
 
-__device__ __forceinline__ int warp_argmax2(int& v, uint32_t& k) {
-  const int vmax = __reduce_max_sync(0xffffffffu, v);
-  const uint32_t kk = (v == vmax) ? k : 0xffffffffu;
-  const uint32_t kmin = __reduce_min_sync(0xffffffffu, kk);
-  const uint32_t win = __ballot_sync(0xffffffffu, kk == kmin && v == vmax);
-  v = vmax;
-  k = kmin;
-  return __ffs(win) - 1;
-}
-
 #ifndef PN2_FB_MAXREG
 #define PN2_FB_MAXREG 64
 #endif
@@ -84,8 +84,8 @@ __global__ void __maxnreg__(PN2_FB_MAXREG) fps_bucket_kernel(const FbArgs a) {
   __shared__ float4 ctr[FB_KMAX];     // accepted centres (x, y, z, key bits)
   __shared__ int ctr_count;
   __shared__ int nwork;
-  __shared__ uint2 w_vk[FB_WARPS];
-  __shared__ float4 w_xyz[FB_WARPS];
+  __shared__ uint2 w_vk[FB_NC];
+  __shared__ float4 w_xyz[FB_NC];
   __shared__ float red[FB_WARPS][6];
   __shared__ float s_org[3], s_scale[3];
 
@@ -184,27 +184,31 @@ __global__ void __maxnreg__(PN2_FB_MAXREG) fps_bucket_kernel(const FbArgs a) {
     for (int k = tid; k < n; k += FB_THREADS) {
       const float x = __ldg(xyz + 3 * k), y = __ldg(xyz + 3 * k + 1), z = __ldg(xyz + 3 * k + 2);
       const int pos = atomicAdd(&cursor[cell_of(x, y, z)], 1);
-      sorted[pos] = make_float4(x, y, z, __int_as_float(k));
+      // .w carries the point's tie-break KEY (fps.cu header), not its index: every bucket update needs the key,
+      // only an accepted sample needs the index back (the accept step inverts the key)
+      const uint32_t u = static_cast<uint32_t>(k);
+      sorted[pos] = make_float4(x, y, z, __uint_as_float((log2bs ? __brev(u & bsmask) : 0u) | (u >> log2bs)));
     }
-    for (int k = n + tid; k < npad; k += FB_THREADS) sorted[k] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    for (int k = n + tid; k < npad; k += FB_THREADS) sorted[k] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xffffffffu));  // no point: no key
     __syncthreads();  // the CTA's own global writes are visible to all its threads from here on
   }
 
   // one bucket (32 * PPL points, PPL per lane): apply the centres in `mask`, refresh temps and the record.
   // `tin` = the running minima of the lane's points (ignored when `init`).
   auto process_bucket = [&](int b, uint32_t mask, bool init, const float4 (&p)[PPL], const float (&tin)[PPL]) {
-    float t[PPL];
-    int o[PPL];
+    float t[PPL], told[PPL];
+    uint32_t key[PPL];
 #pragma unroll
     for (int q = 0; q < PPL; ++q) {
-      o[q] = __float_as_int(p[q].w);
+      key[q] = __float_as_uint(p[q].w);  // 0xffffffff = padding
       if (init) {
         // sampling_gpu.cu:105-106: `if (mag <= 1e-3) continue;` -- a double comparison
         const float mg = __fmaf_rn(p[q].z, p[q].z, __fmaf_rn(p[q].x, p[q].x, __fmul_rn(p[q].y, p[q].y)));
-        t[q] = (o[q] >= 0 && !(static_cast<double>(mg) <= 1e-3)) ? 1e10f : -1.f;
+        t[q] = (key[q] != 0xffffffffu && !(static_cast<double>(mg) <= 1e-3)) ? 1e10f : -1.f;
       } else {
         t[q] = GT ? tin[q] : temps[b * FB_BK + 32 * q + lane];  // shared memory: read on the spot; global: prefetched
       }
+      told[q] = t[q];
     }
     while (mask) {
       const int c = __ffs(mask) - 1;
@@ -213,15 +217,20 @@ __global__ void __maxnreg__(PN2_FB_MAXREG) fps_bucket_kernel(const FbArgs a) {
 #pragma unroll
       for (int q = 0; q < PPL; ++q) t[q] = fminf(sqdist3(p[q].x - oc.x, p[q].y - oc.y, p[q].z - oc.z), t[q]);
     }
+    if (!init) {
+      // the box test is conservative: when no running minimum of the bucket moved, its minima and its record
+      // (a function of them alone) are already right -- skip the stores and the record's three reductions
+      bool moved = false;
+#pragma unroll
+      for (int q = 0; q < PPL; ++q) moved |= t[q] != told[q];
+      if (!__any_sync(0xffffffffu, moved)) return;
+    }
 #pragma unroll
     for (int q = 0; q < PPL; ++q) temps[b * FB_BK + 32 * q + lane] = t[q];
     // lane-local best of its points: value, then smaller key
     int v[PPL];
-    uint32_t key[PPL];
 #pragma unroll
     for (int q = 0; q < PPL; ++q) {
-      const uint32_t u = static_cast<uint32_t>(o[q]);
-      key[q] = o[q] >= 0 ? ((log2bs ? __brev(u & bsmask) : 0u) | (u >> log2bs)) : 0xffffffffu;
       v[q] = __float_as_int(t[q]);  // t >= 0 or exactly -1: int order ok
     }
     int vb = v[0];
@@ -273,17 +282,19 @@ __global__ void __maxnreg__(PN2_FB_MAXREG) fps_bucket_kernel(const FbArgs a) {
     load_bucket(b, p, t, false);
     process_bucket(b, 0u, true, p, t);
   }
-  // thread = bucket, warp = group of GB consecutive buckets.  GB = ceil(nb / 32) spreads the buckets over
-  // all 32 warps: every warp reports a candidate to the acceptance step (32 instead of nb / 32), and the
-  // bound -- the best value no group reported -- comes from smaller groups, so more samples are
-  // accepted per round.
-  const int GB = (nb + FB_WARPS - 1) / FB_WARPS;
-  const int myb = (lane < GB && warp * GB + lane < nb) ? warp * GB + lane : -1;
+  // thread = bucket; a warp holds FB_CPW candidate groups of GB consecutive buckets each (lane segments of FB_GL
+  // lanes).  GB = ceil(nb / FB_NC) spreads the buckets over all warps; the prune step works on the warp's
+  // whole range (one box per warp), the select step on the segments.
+  const int GB = (nb + FB_NC - 1) / FB_NC;  // <= FB_GL: nb <= 1024
+  const int sub = lane / FB_GL, sl = lane % FB_GL;
+  const uint32_t smask = FB_CPW == 1 ? 0xffffffffu : (((1u << FB_GL) - 1u) << (sub * FB_GL));
+  const int cgrp = warp * FB_CPW + sub;
+  const int myb = (sl < GB && cgrp * GB + sl < nb) ? cgrp * GB + sl : -1;
   Box bbox = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
   if (myb >= 0) {
     for (int i = 0; i < FB_BK; ++i) {
       const float4 p = sorted[myb * FB_BK + i];
-      if (__float_as_int(p.w) >= 0) {
+      if (__float_as_uint(p.w) != 0xffffffffu) {
         bbox.lx = fminf(bbox.lx, p.x); bbox.ly = fminf(bbox.ly, p.y); bbox.lz = fminf(bbox.lz, p.z);
         bbox.hx = fmaxf(bbox.hx, p.x); bbox.hy = fmaxf(bbox.hy, p.y); bbox.hz = fmaxf(bbox.hz, p.z);
       }
@@ -306,7 +317,7 @@ __global__ void __maxnreg__(PN2_FB_MAXREG) fps_bucket_kernel(const FbArgs a) {
   __syncthreads();
   float bmax = myb >= 0 ? bb_a[myb].x : -1.f;
   float gmax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(bmax)));
-  const bool has_group = warp * GB < nb;  // warp-uniform
+  const bool has_group = warp * FB_CPW * GB < nb;  // warp-uniform
 
 #ifdef PN2_FB_DEBUG
   long long dbg_items = 0, dbg_t[5] = {0, 0, 0, 0, 0}, dbg_prev = clock64();
@@ -389,21 +400,21 @@ __global__ void __maxnreg__(PN2_FB_MAXREG) fps_bucket_kernel(const FbArgs a) {
         second = __float_as_int(q.y); rz = q.x;
       }
       bmax = __int_as_float(best);
-      const int vmax = __reduce_max_sync(0xffffffffu, best);
-      gmax = __int_as_float(vmax);
+      gmax = __int_as_float(__reduce_max_sync(0xffffffffu, best));  // of the warp's whole range (prune)
+      const int vmax = __reduce_max_sync(smask, best);               // of this lane's candidate group
       const uint32_t kk = (best == vmax) ? bkey : 0xffffffffu;
-      const uint32_t kmin = __reduce_min_sync(0xffffffffu, kk);
+      const uint32_t kmin = __reduce_min_sync(smask, kk);
       const bool win = (kk == kmin) && (best == vmax);
-      const int first = __ffs(__ballot_sync(0xffffffffu, win)) - 1;
+      const int first = __ffs(__ballot_sync(0xffffffffu, win) & smask) - 1;
       const float wx = __shfl_sync(0xffffffffu, r.z, first), wy = __shfl_sync(0xffffffffu, r.w, first),
                   wz = __shfl_sync(0xffffffffu, rz, first);
-      // a neighbouring bucket whose best is an exact coordinate twin of the warp's winner (duplicates
+      // a neighbouring bucket whose best is an exact coordinate twin of the group's winner (duplicates
       // split by a bucket boundary) contributes its `second`, not its best -- same argument as above
       const bool twin = (best == vmax) && (r.z == wx) && (r.w == wy) && (rz == wz);
-      const int wsec = __reduce_max_sync(0xffffffffu, (lane == first || twin) ? second : best);
+      const int wsec = __reduce_max_sync(smask, (lane == first || twin) ? second : best);
       if (lane == first) {
-        w_vk[warp] = make_uint2(static_cast<uint32_t>(vmax), kmin);
-        w_xyz[warp] = make_float4(r.z, r.w, rz, __int_as_float(wsec));
+        w_vk[cgrp] = make_uint2(static_cast<uint32_t>(vmax), kmin);
+        w_xyz[cgrp] = make_float4(r.z, r.w, rz, __int_as_float(wsec));
       }
       if (tid == 0) nwork = 0;
     }
@@ -411,35 +422,57 @@ __global__ void __maxnreg__(PN2_FB_MAXREG) fps_bucket_kernel(const FbArgs a) {
     FB_T(2)
     // ---------------- 4. accept: greedy FPS on the 32 warp candidates (exact) ------------------------
     if (warp == 0) {
-      const uint2 r = w_vk[lane];
-      const float4 w = w_xyz[lane];
-      int cv = static_cast<int>(r.x);
-      const uint32_t ck = r.y;
-      const float cx = w.x, cy = w.y, cz = w.z;
-      const int bnd = max(__reduce_max_sync(0xffffffffu, __float_as_int(w.w)), 0);
+      // lane holds candidates lane + 32 q
+      int cv[FB_CPW];
+      uint32_t ck[FB_CPW];
+      float cx[FB_CPW], cy[FB_CPW], cz[FB_CPW];
+      int lb = __float_as_int(-1.f);
+#pragma unroll
+      for (int q = 0; q < FB_CPW; ++q) {
+        const uint2 r = w_vk[lane + 32 * q];
+        const float4 w = w_xyz[lane + 32 * q];
+        cv[q] = static_cast<int>(r.x); ck[q] = r.y;
+        cx[q] = w.x; cy[q] = w.y; cz[q] = w.z;
+        lb = max(lb, __float_as_int(w.w));
+      }
+      const int bnd = max(__reduce_max_sync(0xffffffffu, lb), 0);
       const int room = min(FB_KMAX, m - j);
       int k = 0;
-      int rv = __reduce_max_sync(0xffffffffu, cv);
+      // the lane's best candidate: value, then smaller key
+      int lv;
+      uint32_t lk;
+      float lx, ly, lz;
+      auto lane_best = [&]() {
+        lv = cv[0]; lk = ck[0]; lx = cx[0]; ly = cy[0]; lz = cz[0];
+#pragma unroll
+        for (int q = 1; q < FB_CPW; ++q)
+          if (cv[q] > lv || (cv[q] == lv && ck[q] < lk)) { lv = cv[q]; lk = ck[q]; lx = cx[q]; ly = cy[q]; lz = cz[q]; }
+      };
+      lane_best();
+      int rv = __reduce_max_sync(0xffffffffu, lv);
       if (rv < 0) {
         // no eligible point anywhere: every reference thread reports besti = 0 (key of index 0 is 0)
         if (lane == 0) ctr[0] = make_float4(x0, y0, z0, __uint_as_float(0u));
         k = 1;
       } else {
         for (;;) {
-          uint32_t tie = __ballot_sync(0xffffffffu, cv == rv);
+          uint32_t tie = __ballot_sync(0xffffffffu, lv == rv);
           if (tie & (tie - 1)) {  // equal values: the smallest key wins (keys are unique)
-            const uint32_t kk = (cv == rv) ? ck : 0xffffffffu;
+            const uint32_t kk = (lv == rv) ? lk : 0xffffffffu;
             const uint32_t kmin = __reduce_min_sync(0xffffffffu, kk);
             tie = __ballot_sync(0xffffffffu, kk == kmin);
           }
           const int src = __ffs(tie) - 1;
-          const float ax = __shfl_sync(0xffffffffu, cx, src), ay = __shfl_sync(0xffffffffu, cy, src),
-                      az = __shfl_sync(0xffffffffu, cz, src);
-          const uint32_t ak = __shfl_sync(0xffffffffu, ck, src);
+          const float ax = __shfl_sync(0xffffffffu, lx, src), ay = __shfl_sync(0xffffffffu, ly, src),
+                      az = __shfl_sync(0xffffffffu, lz, src);
+          const uint32_t ak = __shfl_sync(0xffffffffu, lk, src);
           if (lane == 0) ctr[k] = make_float4(ax, ay, az, __uint_as_float(ak));
           if (++k >= room) break;
-          cv = __float_as_int(fminf(sqdist3(cx - ax, cy - ay, cz - az), __int_as_float(cv)));
-          rv = __reduce_max_sync(0xffffffffu, cv);
+#pragma unroll
+          for (int q = 0; q < FB_CPW; ++q)
+            cv[q] = __float_as_int(fminf(sqdist3(cx[q] - ax, cy[q] - ay, cz[q] - az), __int_as_float(cv[q])));
+          lane_best();
+          rv = __reduce_max_sync(0xffffffffu, lv);
           if (!(rv > bnd)) break;
         }
       }
