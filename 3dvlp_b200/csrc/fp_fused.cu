@@ -107,18 +107,24 @@ fp_prepare_kernel(int n, int m, int c1, int c2, int kpad, const float* __restric
   // ---- 64 channels per pass: lane = point, warp = 16-channel slice; transpose; store ----------
   const int ch_begin = blockIdx.z * FP_CH_PER_CTA, ch_stop = min(kpad, ch_begin + FP_CH_PER_CTA);
   for (int ch0 = ch_begin; ch0 < ch_stop; ch0 += 64) {
+    // every gather of the 16 channels is requested before the first is used (predicated loads, no branches): one
+    // or two global round trips per pass instead of sixteen -- the kernel was 78 % long-scoreboard stalls
+    float x1[16], x2[16], x3[16], xu[16];
 #pragma unroll
     for (int cc = 0; cc < 16; ++cc) {
       const int c = ch0 + warp * 16 + cc;
-      float v = 0.f;
-      if (live) {
-        if (c < c2) {
-          const float* p = kfb + static_cast<size_t>(c) * m;
-          v = __fmaf_rn(__ldg(p + a3), w3, __fmaf_rn(__ldg(p + a1), w1, __fmul_rn(__ldg(p + a2), w2)));
-        } else if (c < c2 + c1) {
-          v = __ldg(ufb + static_cast<size_t>(c - c2) * n + j);
-        }
-      }
+      const bool isk = live && c < c2, isu = live && c >= c2 && c < c2 + c1;
+      const float* p = kfb + static_cast<size_t>(isk ? c : 0) * m;
+      x1[cc] = isk ? __ldg(p + a1) : 0.f;
+      x2[cc] = isk ? __ldg(p + a2) : 0.f;
+      x3[cc] = isk ? __ldg(p + a3) : 0.f;
+      xu[cc] = isu ? __ldg(ufb + static_cast<size_t>(c - c2) * n + j) : 0.f;
+    }
+#pragma unroll
+    for (int cc = 0; cc < 16; ++cc) {
+      const int c = ch0 + warp * 16 + cc;
+      // zero weights on dead lanes / channels would still be exact, but keep the selects explicit
+      const float v = (live && c < c2) ? __fmaf_rn(x3[cc], w3, __fmaf_rn(x1[cc], w1, __fmul_rn(x2[cc], w2))) : xu[cc];
       tile[lane][warp * 16 + cc] = v;
     }
     __syncthreads();
