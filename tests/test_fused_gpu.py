@@ -262,6 +262,29 @@ def test_sa_tiles_per_group_option_is_bit_identical(pkg, cuda, name):
         assert torch.equal(o, outs[0])
 
 
+@pytest.mark.parametrize("c_in", [0, 1, 4])
+def test_sa_four_group_cta_equals_single_group_ctas(pkg, cuda, c_in):
+    """SA1-sized weights run four tile groups in ONE CTA per SM once a call holds >= 4 tiles per SM (the prologue
+    is paid once per SM), and four single-group CTAs per SM below that (csrc/sa_fused.cu, pn2_sa_group_mlp).
+    The batched call (6 x 256 x 64 / 128 = 768 tiles) takes the first layout, each scene alone (128 tiles) the
+    second: same bits."""
+    from common import cloud, fill_state_dict
+    b, n, npoint, ns = 6, 4000, 256, 64
+    pc = cloud(77 + c_in, b, n, c_extra=c_in, extent=1.5, dup_frac=0.05, origin_pts=2)
+    xyz = pc[..., :3].contiguous().to(cuda)
+    feats = (pc[..., 3:].transpose(1, 2).contiguous() * 2.0 - 0.7).to(cuda) if c_in else None
+    m = pkg.PointnetSAModuleVotes(npoint=npoint, radius=0.3, nsample=ns, mlp=[c_in, 64, 64, 128], use_xyz=True,
+                                  normalize_xyz=True)
+    fill_state_dict(m)
+    m = m.to(cuda).eval()
+    with torch.no_grad():
+        _, nf, inds = m(xyz, feats)
+        for i in range(b):
+            _, nf_i, inds_i = m(xyz[i:i + 1].contiguous(), None if feats is None else feats[i:i + 1].contiguous())
+            assert torch.equal(inds_i[0], inds[i])
+            assert torch.equal(nf_i[0], nf[i]), i
+
+
 def test_throughput_graph_equals_latency_graph(pkg, cuda):
     """GraphedBackbone(throughput=True) (bucketed FPS, fewer fused-SA CTAs) == the default graph."""
     import importlib
