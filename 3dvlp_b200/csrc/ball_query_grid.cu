@@ -157,32 +157,40 @@ __device__ __forceinline__ void bq_query_centre(int n, int m, int scene, int j, 
     const int v = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += v;
   }
-  const int total = __shfl_sync(0xffffffffu, incl, 26);
-  if (lane < 27) { s_begin[lane] = begin; s_off[lane] = incl - count; }
-  if (lane == 27) s_off[27] = total;
-  __syncwarp();
-
+  const int total = __shfl_sync(0xffffffffu, incl, 31);  // lanes 27..31 hold no range
+  // the NON-EMPTY ranges, compacted: their exclusive offsets are strictly increasing
   const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t nonempty = __ballot_sync(0xffffffffu, count > 0);
+  const int nr = __popc(nonempty);
+  if (count > 0) {
+    const int slot = __popc(nonempty & lt);
+    s_begin[slot] = begin;
+    s_off[slot] = incl - count;
+  }
+  __syncwarp();
+  const int my_off = lane < nr ? s_off[lane] : 0x7fffffff;
+
   int nhit = 0;
   const bool use_grid = total <= max_total;  // warp-uniform
   if (!use_grid) nhit = BQ_CAP + 1;          // -> the ordered linear scan below
+  int ranges_before = 0;                     // ranges that start before q0
   for (int q0 = 0; use_grid && q0 < total; q0 += 32) {
     const int q = q0 + lane;
+    // which range holds candidate q: every range that starts inside this chunk of 32 candidates sets one bit
+    // (one redux.or for the warp); a lane's range is the last one that starts at or before its candidate --
+    // a population count instead of a five-step binary search over shared memory per candidate
+    const uint32_t rel = static_cast<uint32_t>(my_off - q0);
+    const uint32_t marks = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
     bool hit = false;
     int pidx = 0;
     if (q < total) {
-      // which of the 27 ranges holds candidate q: binary search over the exclusive offsets
-      int lo = 0, hi = 26;
-#pragma unroll
-      for (int it = 0; it < 5; ++it) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (s_off[mid] <= q) lo = mid; else hi = mid - 1;
-      }
+      const int lo = ranges_before + __popc(marks & (0xffffffffu >> (31 - lane))) - 1;
       const float4* pp = pts + s_begin[lo] + (q - s_off[lo]);
       const float4 p = SMEM ? *pp : __ldg(pp);
       hit = sqdist3(cx - p.x, cy - p.y, cz - p.z) < radius2;
       pidx = __float_as_int(p.w);
     }
+    ranges_before += __popc(marks);
     const uint32_t mk = __ballot_sync(0xffffffffu, hit);
     if (hit) {
       const int pos = nhit + __popc(mk & lt);
