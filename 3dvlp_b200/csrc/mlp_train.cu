@@ -281,7 +281,16 @@ struct WgArgs {
   long long rows;
   int c_out, c_in, ld_dy, ld_x, nt;  // nt = columns of this launch's N tile (multiple of 16, <= 256)
   long long chunks_per_cta;
+  // split-precision operands: `terms` bf16 terms (h, m, l) of dy and of x, each term a column block of its row
+  // layout (mlp_train.py _ROW_BLOCKS); all leading (dy term, x term) products accumulate into ONE TMEM tile
+  int terms, blk_dy, blk_x;          // block widths in elements (c_out, ld_x / number of blocks)
 };
+
+// first column block holding term t in the row layouts [h], [h|m|h], [h|m|h|l|h|m]
+__device__ __constant__ int kWgFirstBlock[3] = {0, 1, 3};
+// leading products (dy term, x term) per number of terms: 1, 3, 6 of them
+__device__ __constant__ int kWgProdDy[6] = {0, 1, 0, 2, 0, 1};
+__device__ __constant__ int kWgProdX[6] = {0, 0, 1, 0, 2, 1};
 
 __device__ __forceinline__ void wg_store_tile(uint32_t smem_tile, const __nv_bfloat16* __restrict__ src, int ld,
                                               long long row0, long long rows, int ch0, int ch_count, int tile_rows,
@@ -320,9 +329,10 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgArgs a) {
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_bytes = 128u * 128u, b_bytes = static_cast<uint32_t>(a.nt) * 128u;
-  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
-  const int co0 = blockIdx.y * 128, ci0 = blockIdx.z * 256;
+  const uint32_t a_bytes = 128u * 128u, b_bytes = (static_cast<uint32_t>(a.nt) * 128u + 1023u) & ~1023u;
+  const uint32_t stage_bytes = static_cast<uint32_t>(a.terms) * (a_bytes + b_bytes);  // terms A tiles, then terms B tiles
+  const int n_prod = a.terms == 1 ? 1 : (a.terms == 2 ? 3 : 6);
+  const int co0 = blockIdx.y * 128, ci0 = blockIdx.z * a.nt;  // nz > 1 only with full nt-wide tiles
   const int co_cnt = min(128, a.c_out - co0);                 // multiple of 8
   const int ci_cnt = min(a.nt, ((a.c_in - ci0) + 7) & ~7);      // channels with data (x rows are padded to ld_x)
   uint32_t tmem_cols = 32;
@@ -348,17 +358,25 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgArgs a) {
     // stage s was last read by the MMAs issued two steps ago
     if (n_issued >= 2 && !mbar_wait(&bar_mma[s], ((n_issued - 2) >> 1) & 1)) { failed = true; break; }
     const uint32_t sa = base + s * stage_bytes;
-    wg_store_tile(sa, a.dy, a.ld_dy, ck * 64, a.rows, co0, co_cnt, 128, tid);
-    wg_store_tile(sa + a_bytes, a.x, a.ld_x, ck * 64, a.rows, ci0, ci_cnt, a.nt, tid);
+    const uint32_t sb = sa + static_cast<uint32_t>(a.terms) * a_bytes;
+    // every term of both operands is read ONCE per chunk (one launch per product read each of them up to three times)
+    for (int t = 0; t < a.terms; ++t) {
+      const int blk = kWgFirstBlock[t];
+      wg_store_tile(sa + t * a_bytes, a.dy + blk * a.blk_dy, a.ld_dy, ck * 64, a.rows, co0, co_cnt, 128, tid);
+      wg_store_tile(sb + t * b_bytes, a.x + blk * a.blk_x, a.ld_x, ck * 64, a.rows, ci0, ci_cnt, a.nt, tid);
+    }
     fence_proxy_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     if (tid == 0) {
       tc::fence_after_sync();
+      for (int pr = 0; pr < n_prod; ++pr) {
+        const uint32_t ta = sa + kWgProdDy[pr] * a_bytes, tb = sb + kWgProdX[pr] * b_bytes;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        tc::mma_bf16(tmem_d, tc::smem_desc_sw128(sa + kk * 32), tc::smem_desc_sw128(sa + a_bytes + kk * 32), idesc,
-                     (n_issued > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk)
+          tc::mma_bf16(tmem_d, tc::smem_desc_sw128(ta + kk * 32), tc::smem_desc_sw128(tb + kk * 32), idesc,
+                       (n_issued > 0 || pr > 0 || kk > 0) ? 1u : 0u);
+      }
       tc::mma_commit(&bar_mma[s]);
     }
   }
@@ -515,22 +533,26 @@ extern "C" int pn2_unpack_rows(int b, int c, int n, int ld, long long batch_stri
   return PN2_OK;
 }
 
-extern "C" int pn2_wgrad_bf16(long long rows, int c_out, int c_in, int ld_dy, int ld_x, const void* dy_bf16,
-                              const void* x_bf16, float* dw, void* stream) {
-  PN2_RANGE("pn2_wgrad_bf16");
+static int wgrad_launch(long long rows, int c_out, int c_in, int ld_dy, int ld_x, const void* dy_bf16,
+                        const void* x_bf16, int terms, float* dw, void* stream, const char* who) {
   if (rows <= 0) return PN2_OK;
-  PN2_REQUIRE(c_out > 0 && c_out % 8 == 0 && c_in > 0 && ld_x % 8 == 0 && ld_x >= ((c_in + 7) & ~7) && ld_dy % 8 == 0 &&
-                  ld_dy >= c_out && dy_bf16 && x_bf16 && dw,
-              "wgrad_bf16: bad arguments (c_out %% 8, ld_dy / ld_x %% 8, ld_x >= c_in rounded up to 8)");
+  PN2_REQUIRE(terms >= 1 && terms <= 3, "%s: terms=%d must be 1, 2 or 3", who, terms);
+  const int nblk = terms == 1 ? 1 : (terms == 2 ? 3 : 6);
+  PN2_REQUIRE(c_out > 0 && c_out % 8 == 0 && c_in > 0 && ld_x % (8 * nblk) == 0 && ld_x / nblk >= ((c_in + 7) & ~7) &&
+                  ld_dy % 8 == 0 && ld_dy >= nblk * c_out && dy_bf16 && x_bf16 && dw,
+              "%s: bad arguments (c_out %% 8, ld_dy / ld_x %% 8, every x block >= c_in rounded up to 8)", who);
   PN2_REQUIRE(((reinterpret_cast<uintptr_t>(dy_bf16) | reinterpret_cast<uintptr_t>(x_bf16)) & 15) == 0,
-              "wgrad_bf16: operands must be 16-byte aligned");
+              "%s: operands must be 16-byte aligned", who);
   WgArgs a;
   a.dy = static_cast<const __nv_bfloat16*>(dy_bf16); a.x = static_cast<const __nv_bfloat16*>(x_bf16); a.dw = dw;
   a.rows = rows; a.c_out = c_out; a.c_in = c_in; a.ld_dy = ld_dy; a.ld_x = ld_x;
+  a.terms = terms; a.blk_dy = c_out; a.blk_x = ld_x / nblk;
   a.err = device_err_flag();
-  PN2_REQUIRE(a.err != nullptr, "wgrad_bf16: cannot allocate the device error flag");
-  const int nz = (c_in + 255) / 256, ny = (c_out + 127) / 128;
-  int nt = c_in >= 256 ? 256 : ((c_in + 15) & ~15);
+  PN2_REQUIRE(a.err != nullptr, "%s: cannot allocate the device error flag", who);
+  // N tile: up to 256 input channels, 128 with three terms (two stages of 3 x (16 + 16) KB must fit shared memory)
+  const int nt_max = terms == 3 ? 128 : 256;
+  const int nt = c_in >= nt_max ? nt_max : ((c_in + 15) & ~15);
+  const int nz = (c_in + nt - 1) / nt, ny = (c_out + 127) / 128;
   a.nt = nt;
   const long long chunks = (rows + 63) / 64;
   long long ctas = 2LL * sm_count() / (ny * nz);
@@ -538,11 +560,23 @@ extern "C" int pn2_wgrad_bf16(long long rows, int c_out, int c_in, int ld_dy, in
   if (ctas > chunks) ctas = chunks;
   a.chunks_per_cta = (chunks + ctas - 1) / ctas;
   ctas = (chunks + a.chunks_per_cta - 1) / a.chunks_per_cta;
-  const size_t stage = 128 * 128 + ((static_cast<size_t>(nt) * 128 + 1023) & ~static_cast<size_t>(1023));
+  const size_t stage = static_cast<size_t>(terms) * (128 * 128 + ((static_cast<size_t>(nt) * 128 + 1023) & ~static_cast<size_t>(1023)));
   const size_t smem = 2 * stage + 1024;
   PN2_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>(ctas), ny, nz);
   wgrad_kernel<<<grid, WG_THREADS, smem, as_stream(stream)>>>(a);
   PN2_CHECK_LAUNCH("wgrad_kernel");
   return PN2_OK;
+}
+
+extern "C" int pn2_wgrad_bf16(long long rows, int c_out, int c_in, int ld_dy, int ld_x, const void* dy_bf16,
+                              const void* x_bf16, float* dw, void* stream) {
+  PN2_RANGE("pn2_wgrad_bf16");
+  return wgrad_launch(rows, c_out, c_in, ld_dy, ld_x, dy_bf16, x_bf16, 1, dw, stream, "wgrad_bf16");
+}
+
+extern "C" int pn2_wgrad_split_bf16(long long rows, int c_out, int c_in, int ld_dy, int ld_x, const void* dy_bf16,
+                                    const void* x_bf16, int terms, float* dw, void* stream) {
+  PN2_RANGE("pn2_wgrad_split_bf16");
+  return wgrad_launch(rows, c_out, c_in, ld_dy, ld_x, dy_bf16, x_bf16, terms, dw, stream, "wgrad_split_bf16");
 }

@@ -211,13 +211,10 @@ class _SharedMLPMaxPool(Function):
                    device=dev)
             dW = torch.zeros(co, ci, device=dev, dtype=torch.float32)
             kx = X.shape[1] // blocks                        # width of one operand block of X
-            # dW = dY^T X: one launch per leading (dY term, X term) product, on the column blocks holding the terms
-            first = {t: _ROW_BLOCKS[split].index(t) for t in set(_ROW_BLOCKS[split])}   # term -> first block
-            for dy_t, x_t in set(zip(_ROW_BLOCKS[split], _W_BLOCKS[split])):
-                dy_blk, x_blk = first[dy_t], first[x_t]
-                L.call("pn2_wgrad_bf16", _ll(P), co, ci, blocks * co, blocks * kx,
-                       ctypes.c_void_p(dY.data_ptr() + 2 * dy_blk * co), ctypes.c_void_p(X.data_ptr() + 2 * x_blk * kx),
-                       L.ptr(dW), st, device=dev)
+            # dW = dY^T X: ONE launch for all leading (dY term, X term) products -- every term block of both
+            # operands is read once and the products accumulate into one TMEM tile (csrc/mlp_train.cu)
+            L.call("pn2_wgrad_split_bf16", _ll(P), co, ci, blocks * co, blocks * kx, L.ptr(dY), L.ptr(X), split,
+                   L.ptr(dW), st, device=dev)
             grads[3 * i] = dW.view_as(w)
             if i == 0 and not ctx.needs_input_grad[0]:
                 break

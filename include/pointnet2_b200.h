@@ -318,9 +318,17 @@ int pn2_bn_bwd_rows(long long rows, int c, int ld_da, int ld_y, const float* da,
 /* dw[co][ci] += sum_r dy[r][co] * x[r][ci] on tcgen05 (bf16 operands, fp32 accumulation, fp32 atomics):
  * dy (rows, ld_dy) bf16 columns [0, c_out), x (rows, ld_x) bf16 columns [0, c_in), dw (c_out, c_in) fp32 --
  * caller zero-fills.  c_out % 8 == 0, ld_dy % 8 == 0, ld_x % 8 == 0, ld_x >= c_in rounded up to 8; pointers
- * 16-byte aligned.  Split-precision gradients are three calls on the h / l column blocks of the operands. */
+ * 16-byte aligned. */
 int pn2_wgrad_bf16(long long rows, int c_out, int c_in, int ld_dy, int ld_x, const void* dy_bf16,
                    const void* x_bf16, float* dw, void* stream);
+
+/* The same contraction on split-precision operands in ONE launch: dy and x are rows in the `terms` layout of
+ * pn2_bn_relu_rows / pn2_bn_bwd_rows (terms = 1: [h]; 2: [h|m|h]; 3: [h|m|h|l|h|m]; dy blocks c_out wide, x blocks
+ * ld_x / {1, 3, 6} wide).  Every term of both operands is read once per 64-row chunk and all leading
+ * (dy term, x term) products -- 1, 3 or 6 -- accumulate into one TMEM tile: against one pn2_wgrad_bf16 call per
+ * product, half the operand traffic and a sixth of the launches / fp32 atomics at terms = 3. */
+int pn2_wgrad_split_bf16(long long rows, int c_out, int c_in, int ld_dy, int ld_x, const void* dy_bf16,
+                         const void* x_bf16, int terms, float* dw, void* stream);
 
 /* rows (b*n, ld) fp32, columns [0, c) -> out[b][ch][p] at out + b*batch_stride + ch*n + p: the gradient
  * w.r.t. a (B, C, n) tensor (or a channel slice of one) from its point-major form. */

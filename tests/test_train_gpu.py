@@ -215,3 +215,47 @@ def test_backbone_train_step_vs_reference_golden(pkg, gold, cuda):
         assert ours[1][n] < max(2.5 * ref[1][n], 2e-2), (n, ours[1][n], ref[1][n])
     for n in BB_STATS:
         assert ours[2][n] < max(2.5 * ref[2][n], 1e-3), (n, ours[2][n], ref[2][n])
+
+
+def _split_rows(a, terms):
+    """fp32 (rows, c) -> bf16 rows in the `terms` layout of the training kernels: [h], [h|m|h], [h|m|h|l|h|m]."""
+    h = a.bfloat16()
+    r1 = a - h.float()
+    m = r1.bfloat16()
+    lo = (r1 - m.float()).bfloat16()
+    t = (h, m, lo)
+    order = {1: (0,), 2: (0, 1, 0), 3: (0, 1, 0, 2, 0, 1)}[terms]
+    return torch.cat([t[i] for i in order], dim=1).contiguous(), t
+
+
+@pytest.mark.parametrize("terms", [1, 2, 3])
+@pytest.mark.parametrize("rows,c_out,c_in", [(5000, 64, 4), (4100, 128, 64), (3000, 256, 259), (130, 64, 131)])
+def test_wgrad_split_one_launch(pkg, cuda, terms, rows, c_out, c_in):
+    """pn2_wgrad_split_bf16: every leading (dy term, x term) product of the split-precision weight gradient in one
+    launch, accumulated in one TMEM tile -- against the fp64 sum of the same bf16 term products (the contraction is
+    exact up to fp32 accumulation) and against one pn2_wgrad_bf16 call per product."""
+    import ctypes
+    L = pkg._lib
+    g = torch.Generator().manual_seed(rows + c_in)
+    dy32 = (torch.randn(rows, c_out, generator=g) * 0.3).to(cuda)
+    kx = (c_in + 15) // 16 * 16
+    x32 = torch.zeros(rows, kx, device=cuda)
+    x32[:, :c_in] = torch.rand(rows, c_in, generator=g).to(cuda) * 2 - 0.5
+    dy, dyt = _split_rows(dy32, terms)
+    x, xt = _split_rows(x32, terms)
+    prods = {1: [(0, 0)], 2: [(0, 0), (1, 0), (0, 1)], 3: [(0, 0), (1, 0), (0, 1), (2, 0), (0, 2), (1, 1)]}[terms]
+    want = sum(dyt[i].double().t() @ xt[j].double()[:, :c_in] for i, j in prods)
+    nblk = {1: 1, 2: 3, 3: 6}[terms]
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    dw = torch.zeros(c_out, c_in, device=cuda)
+    L.call("pn2_wgrad_split_bf16", ctypes.c_longlong(rows), c_out, c_in, nblk * c_out, nblk * kx, L.ptr(dy), L.ptr(x),
+           terms, L.ptr(dw), st, device=cuda)
+    scale = float(want.abs().max())
+    assert float((dw.double() - want).abs().max()) <= 2e-5 * scale
+    first = {0: 0, 1: 1, 2: 3}
+    dw6 = torch.zeros(c_out, c_in, device=cuda)
+    for i, j in prods:
+        L.call("pn2_wgrad_bf16", ctypes.c_longlong(rows), c_out, c_in, nblk * c_out, nblk * kx,
+               ctypes.c_void_p(dy.data_ptr() + 2 * first[i] * c_out), ctypes.c_void_p(x.data_ptr() + 2 * first[j] * kx),
+               L.ptr(dw6), st, device=cuda)
+    assert float((dw - dw6).abs().max()) <= 2e-5 * scale
