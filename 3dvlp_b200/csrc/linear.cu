@@ -26,7 +26,12 @@ struct LinArgs {
   void* y;
   int* err;
   int m, n, k, relu, out_mode, rows_per_batch;
+  // split-precision rows (training, csrc/mlp_train.cu): x stores `terms` blocks of kb columns, [h|m] or [h|m|l];
+  // the logical K of the contraction is 3 or 6 blocks -- logical block i reads stored block kLinRowBlock[i]
+  int terms, kb, ldx;
 };
+
+__device__ __constant__ int kLinRowBlock[6] = {0, 1, 0, 2, 0, 1};  // the first three entries serve terms = 2
 
 __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const LinArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -58,6 +63,11 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const LinArgs a) {
 
   auto load = [&](int kc, int s) {
     const uint32_t sa = base + s * stage_bytes;
+    int col = kc * 64;  // first stored column of the chunk
+    if (a.terms > 1) {
+      const int cpb = a.kb >> 6, blk = kc / cpb;
+      col = kLinRowBlock[blk] * a.kb + (kc - blk * cpb) * 64;
+    }
     if (tid == 0) {
       mbar_arrive_expect_tx(&bar_w[s], w_bytes);
       // generic pointer of the stage's W region: offset from the dynamic smem base
@@ -69,7 +79,7 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const LinArgs a) {
       const int q = i * LIN_THREADS + tid;
       const int r = q >> 3, j = q & 7;
       const bool ok = row0 + r < a.m;
-      const __nv_bfloat16* src = a.x + static_cast<size_t>(ok ? row0 + r : 0) * a.k + kc * 64 + j * 8;
+      const __nv_bfloat16* src = a.x + static_cast<size_t>(ok ? row0 + r : 0) * a.ldx + col + j * 8;
       tc::cp_async16(sa + tc::swz_off(r, j), src, ok);
     }
     tc::cp_async_commit();
@@ -204,8 +214,8 @@ pack_rows64_kernel(int c, int n, int kpad, const float* __restrict__ f, __nv_bfl
   }
 }
 
-// pack_rows64_kernel in the split layouts of csrc/mlp_train.cu (store_rows8): terms 2 -> (b*n, 3*kpad) rows
-// [h | l | h]; terms 3 -> (b*n, 6*kpad) rows [h | m | h | l | h | m]
+// pack_rows64_kernel in the split layouts of csrc/mlp_train.cu (store_rows8): terms 2 -> (b*n, 2*kpad) rows
+// [h | m]; terms 3 -> (b*n, 3*kpad) rows [h | m | l]
 __global__ void __launch_bounds__(256)
 pack_rows64_split_kernel(int c, int n, int kpad, int terms, const float* __restrict__ f, __nv_bfloat16* __restrict__ out) {
   __shared__ float tile[64][33];
@@ -234,16 +244,10 @@ pack_rows64_split_kernel(int c, int n, int kpad, int terms, const float* __restr
     }
     const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), mv = make_uint4(m[0], m[1], m[2], m[3]),
                 lv = make_uint4(l[0], l[1], l[2], l[3]);
-    const int blocks = terms == 2 ? 3 : 6;
-    __nv_bfloat16* row = out + (static_cast<size_t>(b) * n + p) * blocks * kpad + ch0;
+    __nv_bfloat16* row = out + (static_cast<size_t>(b) * n + p) * terms * kpad + ch0;
     *reinterpret_cast<uint4*>(row) = hv;
     *reinterpret_cast<uint4*>(row + kpad) = mv;
-    *reinterpret_cast<uint4*>(row + 2 * kpad) = hv;
-    if (terms == 3) {
-      *reinterpret_cast<uint4*>(row + 3 * kpad) = lv;
-      *reinterpret_cast<uint4*>(row + 4 * kpad) = hv;
-      *reinterpret_cast<uint4*>(row + 5 * kpad) = mv;
-    }
+    if (terms == 3) *reinterpret_cast<uint4*>(row + 2 * kpad) = lv;
   }
 }
 
@@ -321,23 +325,41 @@ extern "C" int pn2_pack_point_rows_bf16(long long rows, int ld, int col0, int c,
   return PN2_OK;
 }
 
-extern "C" int pn2_linear_bf16(int m, int n, int k, const void* x_bf16, const void* w_packed, const float* bias,
-                               int relu, int out_mode, int rows_per_batch, void* y, void* stream) {
-  PN2_RANGE("pn2_linear_bf16");
+static int linear_launch(int m, int n, int k, int terms, int kb, const void* x_bf16, const void* w_packed,
+                         const float* bias, int relu, int out_mode, int rows_per_batch, void* y, void* stream,
+                         const char* who) {
   if (m <= 0) return PN2_OK;
-  PN2_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0, "linear_bf16: n=%d must be a multiple of 16 in [16,256]", n);
-  PN2_REQUIRE(k >= 64 && k % 64 == 0, "linear_bf16: k=%d must be a positive multiple of 64", k);
-  PN2_REQUIRE(x_bf16 && w_packed && y && out_mode >= 0 && out_mode <= 2, "linear_bf16: bad arguments");
-  PN2_REQUIRE(out_mode != 2 || rows_per_batch > 0, "linear_bf16: rows_per_batch required for channel-major output");
+  PN2_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0, "%s: n=%d must be a multiple of 16 in [16,256]", who, n);
+  PN2_REQUIRE(k >= 64 && k % 64 == 0, "%s: k=%d must be a positive multiple of 64", who, k);
+  PN2_REQUIRE(x_bf16 && w_packed && y && out_mode >= 0 && out_mode <= 2, "%s: bad arguments", who);
+  PN2_REQUIRE(out_mode != 2 || rows_per_batch > 0, "%s: rows_per_batch required for channel-major output", who);
   LinArgs a;
   a.x = static_cast<const __nv_bfloat16*>(x_bf16); a.w = static_cast<const uint8_t*>(w_packed); a.bias = bias;
   a.y = y; a.m = m; a.n = n; a.k = k; a.relu = relu; a.out_mode = out_mode; a.rows_per_batch = rows_per_batch;
+  a.terms = terms; a.kb = kb; a.ldx = terms > 1 ? terms * kb : k;
   a.err = device_err_flag();
-  PN2_REQUIRE(a.err != nullptr, "linear_bf16: cannot allocate the device error flag");
+  PN2_REQUIRE(a.err != nullptr, "%s: cannot allocate the device error flag", who);
   const size_t stage = 128 * 128 + ((static_cast<size_t>(n) * 128 + 1023) & ~static_cast<size_t>(1023));
   const size_t smem = 2 * stage + 1024;
   PN2_CUDA(cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   linear_kernel<<<(m + 127) / 128, LIN_THREADS, smem, as_stream(stream)>>>(a);
   PN2_CHECK_LAUNCH("linear_kernel");
   return PN2_OK;
+}
+
+extern "C" int pn2_linear_bf16(int m, int n, int k, const void* x_bf16, const void* w_packed, const float* bias,
+                               int relu, int out_mode, int rows_per_batch, void* y, void* stream) {
+  PN2_RANGE("pn2_linear_bf16");
+  return linear_launch(m, n, k, 1, k, x_bf16, w_packed, bias, relu, out_mode, rows_per_batch, y, stream, "linear_bf16");
+}
+
+extern "C" int pn2_linear_split_bf16(int m, int n, int kb, int terms, const void* x_bf16, const void* w_packed,
+                                     const float* bias, int relu, int out_mode, int rows_per_batch, void* y,
+                                     void* stream) {
+  PN2_RANGE("pn2_linear_split_bf16");
+  PN2_REQUIRE(terms >= 1 && terms <= 3 && kb >= 64 && kb % 64 == 0,
+              "linear_split_bf16: terms=%d must be 1..3 and kb=%d a positive multiple of 64", terms, kb);
+  const int nblk = terms == 1 ? 1 : (terms == 2 ? 3 : 6);
+  return linear_launch(m, n, nblk * kb, terms, kb, x_bf16, w_packed, bias, relu, out_mode, rows_per_batch, y, stream,
+                       "linear_split_bf16");
 }

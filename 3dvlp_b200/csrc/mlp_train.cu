@@ -102,9 +102,11 @@ __global__ void bn_frozen_kernel(int c, const float* __restrict__ gamma, const f
 // (h = bf16(v), m = bf16(v - h), l = bf16(v - h - m): 8, 16, 24 mantissa bits) laid out along K so that ONE
 // K-concatenated GEMM against a weight laid out in the matching order evaluates the leading products, each
 // exact in the fp32 accumulator:
-//   terms 1   [h]                      x [w_h]                                       plain bf16
-//   terms 2   [h | l | h]              x [w_h | w_h | w_l]            (here l = bf16(v - h))   ~2^-16
-//   terms 3   [h | m | h | l | h | m]  x [w_h | w_h | w_m | w_h | w_l | w_m]                   ~2^-24 (fp32 level)
+//   terms 1   K blocks [h]                      x [w_h]                                       plain bf16
+//   terms 2   K blocks [h | m | h]              x [w_h | w_h | w_m]                                    ~2^-16
+//   terms 3   K blocks [h | m | h | l | h | m]  x [w_h | w_h | w_m | w_h | w_l | w_m]                   ~2^-24 (fp32 level)
+// The WEIGHTS are stored with their K blocks spelled out (they are small); the ROWS store each term once
+// ([h], [h | m], [h | m | l]) and the kernels map a logical K block to the stored one.
 __device__ __forceinline__ void store_rows8(__nv_bfloat16* __restrict__ dst, long long r, int c, int ch0, const float (&o)[8],
                                             int terms) {
   uint32_t h[4], m[4], l[4];
@@ -119,22 +121,12 @@ __device__ __forceinline__ void store_rows8(__nv_bfloat16* __restrict__ dst, lon
   }
   const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), mv = make_uint4(m[0], m[1], m[2], m[3]),
               lv = make_uint4(l[0], l[1], l[2], l[3]);
-  if (terms <= 1) {
-    *reinterpret_cast<uint4*>(dst + r * c + ch0) = hv;
-  } else if (terms == 2) {
-    __nv_bfloat16* row = dst + r * 3 * c + ch0;
-    *reinterpret_cast<uint4*>(row) = hv;
-    *reinterpret_cast<uint4*>(row + c) = mv;
-    *reinterpret_cast<uint4*>(row + 2 * c) = hv;
-  } else {
-    __nv_bfloat16* row = dst + r * 6 * c + ch0;
-    *reinterpret_cast<uint4*>(row) = hv;
-    *reinterpret_cast<uint4*>(row + c) = mv;
-    *reinterpret_cast<uint4*>(row + 2 * c) = hv;
-    *reinterpret_cast<uint4*>(row + 3 * c) = lv;
-    *reinterpret_cast<uint4*>(row + 4 * c) = hv;
-    *reinterpret_cast<uint4*>(row + 5 * c) = mv;
-  }
+  // each term is stored ONCE, [h], [h | m] or [h | m | l]: the contractions address the blocks through the product
+  // tables (linear.cu kLinRowBlock, kWgProd* below) instead of reading duplicated copies
+  __nv_bfloat16* row = dst + r * (terms <= 1 ? 1 : terms) * c + ch0;
+  *reinterpret_cast<uint4*>(row) = hv;
+  if (terms >= 2) *reinterpret_cast<uint4*>(row + c) = mv;
+  if (terms >= 3) *reinterpret_cast<uint4*>(row + 2 * c) = lv;
 }
 
 // X' = relu(Y * scale + shift) as operand rows, thread = 8 channels of one row
@@ -282,12 +274,10 @@ struct WgArgs {
   int c_out, c_in, ld_dy, ld_x, nt;  // nt = columns of this launch's N tile (multiple of 16, <= 256)
   long long chunks_per_cta;
   // split-precision operands: `terms` bf16 terms (h, m, l) of dy and of x, each term a column block of its row
-  // layout (mlp_train.py _ROW_BLOCKS); all leading (dy term, x term) products accumulate into ONE TMEM tile
-  int terms, blk_dy, blk_x;          // block widths in elements (c_out, ld_x / number of blocks)
+  // layout ([h], [h|m], [h|m|l]); all leading (dy term, x term) products accumulate into ONE TMEM tile
+  int terms, blk_dy, blk_x;          // block widths in elements (c_out, ld_x / terms)
 };
 
-// first column block holding term t in the row layouts [h], [h|m|h], [h|m|h|l|h|m]
-__device__ __constant__ int kWgFirstBlock[3] = {0, 1, 3};
 // leading products (dy term, x term) per number of terms: 1, 3, 6 of them
 __device__ __constant__ int kWgProdDy[6] = {0, 1, 0, 2, 0, 1};
 __device__ __constant__ int kWgProdX[6] = {0, 0, 1, 0, 2, 1};
@@ -361,7 +351,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgArgs a) {
     const uint32_t sb = sa + static_cast<uint32_t>(a.terms) * a_bytes;
     // every term of both operands is read ONCE per chunk (one launch per product read each of them up to three times)
     for (int t = 0; t < a.terms; ++t) {
-      const int blk = kWgFirstBlock[t];
+      const int blk = t;
       wg_store_tile(sa + t * a_bytes, a.dy + blk * a.blk_dy, a.ld_dy, ck * 64, a.rows, co0, co_cnt, 128, tid);
       wg_store_tile(sb + t * b_bytes, a.x + blk * a.blk_x, a.ld_x, ck * 64, a.rows, ci0, ci_cnt, a.nt, tid);
     }
@@ -537,7 +527,7 @@ static int wgrad_launch(long long rows, int c_out, int c_in, int ld_dy, int ld_x
                         const void* x_bf16, int terms, float* dw, void* stream, const char* who) {
   if (rows <= 0) return PN2_OK;
   PN2_REQUIRE(terms >= 1 && terms <= 3, "%s: terms=%d must be 1, 2 or 3", who, terms);
-  const int nblk = terms == 1 ? 1 : (terms == 2 ? 3 : 6);
+  const int nblk = terms;  // stored blocks per row
   PN2_REQUIRE(c_out > 0 && c_out % 8 == 0 && c_in > 0 && ld_x % (8 * nblk) == 0 && ld_x / nblk >= ((c_in + 7) & ~7) &&
                   ld_dy % 8 == 0 && ld_dy >= nblk * c_out && dy_bf16 && x_bf16 && dw,
               "%s: bad arguments (c_out %% 8, ld_dy / ld_x %% 8, every x block >= c_in rounded up to 8)", who);

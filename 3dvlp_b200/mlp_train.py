@@ -38,8 +38,10 @@ from . import tensorcore as tcm
 _BACKEND = ["tcgen05"]   # or "torch": the reference's cuDNN layers (fp32), kept for semantic cross-checks
 _PRECISION = ["bf16x6"]  # or "bf16x3", "bf16"
 _TERMS = {"bf16": 1, "bf16x3": 2, "bf16x6": 3}
-# K-block order of the operand rows / of the weights per number of terms (0 = h, 1 = m, 2 = l): block i of the
-# rows meets block i of the weight; (row term, weight term) pairs = the leading products
+# LOGICAL K-block order of the operand rows / of the weights per number of terms (0 = h, 1 = m, 2 = l): block i of
+# the rows meets block i of the weight; (row term, weight term) pairs = the leading products.  The weights are stored
+# with these blocks spelled out; the rows store each term ONCE ([h], [h | m], [h | m | l]) and the kernels map a
+# logical block to the stored one (csrc/linear.cu kLinRowBlock, csrc/mlp_train.cu kWgProd*)
 _ROW_BLOCKS = {1: (0,), 2: (0, 1, 0), 3: (0, 1, 0, 2, 0, 1)}
 _W_BLOCKS = {1: (0,), 2: (0, 0, 1), 3: (0, 0, 1, 0, 2, 1)}
 
@@ -117,11 +119,11 @@ def _pack_weight(w2d, kpad, terms):
 
 
 def _pack_input(x3, kpad, terms):
-    """(B, C, n) fp32 channel-major -> operand rows (B*n, blocks * kpad) in the layout of `terms`."""
+    """(B, C, n) fp32 channel-major -> operand rows (B*n, terms * kpad): each bf16 term stored once, [h | m | l]."""
     if terms == 1:
         return tcm.pack_rows(x3, kpad)
     b, c, n = x3.shape
-    out = torch.empty(b * n, len(_ROW_BLOCKS[terms]) * kpad, device=x3.device, dtype=torch.bfloat16)
+    out = torch.empty(b * n, terms * kpad, device=x3.device, dtype=torch.bfloat16)
     L.call("pn2_pack_rows_split_bf16", b, c, n, kpad, terms, L.ptr(x3), L.ptr(out), L.stream_of(x3), device=x3.device)
     return out
 
@@ -143,13 +145,13 @@ class _SharedMLPMaxPool(Function):
         xs, ys, affine = [], [], []
         split = _TERMS[_PRECISION[0]]       # number of bf16 terms per operand
         kw = tcm.kpad64(C0)                                                           # width of one operand block
-        X = _pack_input(x.reshape(B, C0, M * S).contiguous(), kw, split)              # (P, kw) or (P, 3 kw) bf16
+        X = _pack_input(x.reshape(B, C0, M * S).contiguous(), kw, split)              # (P, split * kw) bf16
         out = arg = None
         for i, bn in enumerate(bns):
             w, gamma, beta = params[3 * i], params[3 * i + 1], params[3 * i + 2]
             co = w.shape[0]
             wp = _pack_weight(w.detach().reshape(co, -1).float(), kw, split)
-            Y = tcm.linear(X, wp, None, relu=False, out="f32")                        # (P, co) fp32
+            Y = tcm.linear(X, wp, None, relu=False, out="f32", terms=split)           # (P, co) fp32
             aff = torch.empty(4, co, device=dev, dtype=torch.float32)                 # scale, shift, mean, invstd
             if training:
                 stats = torch.zeros(2, co, device=dev, dtype=torch.float64)
@@ -166,7 +168,7 @@ class _SharedMLPMaxPool(Function):
                        L.ptr(aff[3]), st, device=dev)
             xs.append(X); ys.append(Y); affine.append(aff)
             if i + 1 < n_layers:
-                X = torch.empty(P, len(_ROW_BLOCKS[split]) * co, device=dev, dtype=torch.bfloat16)
+                X = torch.empty(P, split * co, device=dev, dtype=torch.bfloat16)
                 L.call("pn2_bn_relu_rows", _ll(P), co, co, L.ptr(Y), L.ptr(aff[0]), L.ptr(aff[1]), split, L.ptr(X), st,
                        device=dev)
                 kw = co
@@ -203,7 +205,7 @@ class _SharedMLPMaxPool(Function):
                    L.ptr(aff[3]), L.ptr(s[0]), L.ptr(s[1]), st, device=dev)
             grads[3 * i + 1] = s[1].float()   # d gamma = sum dYhat * xhat
             grads[3 * i + 2] = s[0].float()   # d beta  = sum dYhat
-            blocks = len(_ROW_BLOCKS[split])
+            blocks = split                                   # stored term blocks per row: [h | m | l]
             dY = torch.empty(P, blocks * co, device=dev, dtype=torch.bfloat16)
             L.call("pn2_bn_bwd_rows", _ll(P), co, ld_da, co, L.ptr(da), L.ptr(dout if da is None else None),
                    L.ptr(arg if da is None else None), S, M, L.ptr(Y), L.ptr(aff[0]), L.ptr(aff[1]), L.ptr(aff[2]),
@@ -227,7 +229,7 @@ class _SharedMLPMaxPool(Function):
                 rows_pad = (c1 - c0 + 15) // 16 * 16
                 blk = torch.zeros(rows_pad, co, device=dev, dtype=torch.float32)
                 blk[:c1 - c0] = wt[c0:c1]
-                pieces.append((c0, c1, rows_pad, tcm.linear(dY, _pack_weight(blk, co, split), None, relu=False, out="f32")))
+                pieces.append((c0, c1, rows_pad, tcm.linear(dY, _pack_weight(blk, co, split), None, relu=False, out="f32", terms=split)))
             if i > 0:
                 assert len(pieces) == 1   # hidden widths are <= 256
                 da, ld_da = pieces[0][3], pieces[0][2]

@@ -45,12 +45,17 @@ def pack_point_rows(pc, col0, c, kpad=None):
     return out
 
 
-def linear(x, w, bias=None, relu=False, out="f32", rows_per_batch=0, y=None):
+def linear(x, w, bias=None, relu=False, out="f32", rows_per_batch=0, y=None, terms=1):
     """act(x @ W^T + bias) on tensor cores.  x (M, kpad) bf16; w PackedWeight; out in
-    {"f32": (M,n) fp32, "bf16": (M,n) bf16, "cm": (M/rows_per_batch, n, rows_per_batch) fp32}."""
+    {"f32": (M,n) fp32, "bf16": (M,n) bf16, "cm": (M/rows_per_batch, n, rows_per_batch) fp32}.
+    ``terms`` > 1 (training, mlp_train.py): x holds split-precision rows, each bf16 term stored once --
+    (M, terms * kb) as [h | m] or [h | m | l] -- while w spells out the 3 or 6 K blocks of the leading products
+    (w.kpad = 3 kb or 6 kb); the kernel maps a logical K block to the stored one."""
     L.require_cuda_path(x)
-    if x.dtype != torch.bfloat16 or not x.is_contiguous() or x.shape[1] != w.kpad:
-        raise RuntimeError("linear: x must be a contiguous bf16 (M, %d) tensor" % w.kpad)
+    nblk = {1: 1, 2: 3, 3: 6}[terms]
+    kb = w.kpad // nblk
+    if x.dtype != torch.bfloat16 or not x.is_contiguous() or x.shape[1] != terms * kb or kb * nblk != w.kpad:
+        raise RuntimeError("linear: x must be a contiguous bf16 (M, %d) tensor" % (terms * kb))
     m = x.shape[0]
     mode = {"f32": 0, "bf16": 1, "cm": 2}[out]
     if y is not None:  # caller-provided output (e.g. a view into a buffer that leaves the device in one copy)
@@ -64,8 +69,12 @@ def linear(x, w, bias=None, relu=False, out="f32", rows_per_batch=0, y=None):
         y = torch.empty(m, w.n, device=x.device, dtype=torch.bfloat16)
     else:
         y = torch.empty(m // rows_per_batch, w.n, rows_per_batch, device=x.device, dtype=torch.float32)
-    L.call("pn2_linear_bf16", m, w.n, w.kpad, L.ptr(x), L.ptr(w.data), L.ptr(bias), int(bool(relu)), mode,
-           int(rows_per_batch), L.ptr(y), L.stream_of(x), device=x.device)
+    if terms == 1:
+        L.call("pn2_linear_bf16", m, w.n, w.kpad, L.ptr(x), L.ptr(w.data), L.ptr(bias), int(bool(relu)), mode,
+               int(rows_per_batch), L.ptr(y), L.stream_of(x), device=x.device)
+    else:
+        L.call("pn2_linear_split_bf16", m, w.n, kb, terms, L.ptr(x), L.ptr(w.data), L.ptr(bias), int(bool(relu)), mode,
+               int(rows_per_batch), L.ptr(y), L.stream_of(x), device=x.device)
     return y
 
 

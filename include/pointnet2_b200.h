@@ -201,6 +201,12 @@ int pn2_pack_point_rows_bf16(long long rows, int ld, int col0, int c, int kpad, 
 int pn2_linear_bf16(int m, int n, int k, const void* x_bf16, const void* w_packed, const float* bias,
                     int relu, int out_mode, int rows_per_batch, void* y, void* stream);
 
+/* pn2_linear_bf16 on split-precision rows (training): x (m, terms * kb) bf16 stores each term once ([h | m | l],
+ * blocks kb wide, kb % 64 == 0); w_packed holds 1, 3 or 6 K blocks of width kb in the product order given at
+ * pn2_bn_relu_rows; logical K = {1, 3, 6} * kb. */
+int pn2_linear_split_bf16(int m, int n, int kb, int terms, const void* x_bf16, const void* w_packed,
+                          const float* bias, int relu, int out_mode, int rows_per_batch, void* y, void* stream);
+
 /* Fused body of a set-abstraction layer (pointnet2_modules.py:243-257: QueryAndGroup -> SharedMLP
  * (3 layers) -> max_pool2d over nsample), eval mode, BatchNorm folded.  Grouping, the three 1x1
  * convolutions and the max-pool run in one kernel; only the pooled result is written.
@@ -277,17 +283,18 @@ int pn2_bn_finalize(int c, long long count, const double* sum, const double* sum
                     float* scale, float* shift, float* mean, float* invstd, void* stream);
 
 /* Operand rows x = relu(y * scale + shift) of the next contraction: (rows, ld) fp32 -> bf16, c % 8 == 0.
- * A value is carried as `terms` bf16 terms (h = bf16(x), m = bf16(x - h), l = bf16(x - h - m)) laid out along K
- * so that ONE K-concatenated pn2_linear_bf16 against a weight laid out in the matching order evaluates the
- * leading products, each exact in the fp32 accumulator:
- *   terms 1: (rows, c)   [h]                      x [w_h]                                   plain bf16
- *   terms 2: (rows, 3c)  [h | m | h]              x [w_h | w_h | w_m]                       ~2^-16 relative
- *   terms 3: (rows, 6c)  [h | m | h | l | h | m]  x [w_h | w_h | w_m | w_h | w_l | w_m]     ~2^-24 (fp32 level) */
+ * A value is carried as `terms` bf16 terms (h = bf16(x), m = bf16(x - h), l = bf16(x - h - m)), each stored ONCE
+ * per row: (rows, c) [h], (rows, 2c) [h | m] or (rows, 3c) [h | m | l].  pn2_linear_split_bf16 contracts them
+ * against a weight whose K blocks spell out the leading products, each exact in the fp32 accumulator:
+ *   terms 1: K blocks [h]                      x [w_h]                                   plain bf16
+ *   terms 2: K blocks [h | m | h]              x [w_h | w_h | w_m]                       ~2^-16 relative
+ *   terms 3: K blocks [h | m | h | l | h | m]  x [w_h | w_h | w_m | w_h | w_l | w_m]     ~2^-24 (fp32 level)
+ * (the kernel maps a logical K block of the rows to the stored term block). */
 int pn2_bn_relu_rows(long long rows, int c, int ld, const float* y, const float* scale, const float* shift,
                      int terms, void* x_bf16, void* stream);
 
 /* pn2_pack_rows_bf16 in the split layouts above (terms 2 or 3, blocks of width kpad): features (b,c,n) fp32 ->
- * (b*n, 3*kpad) or (b*n, 6*kpad) bf16 rows. */
+ * (b*n, 2*kpad) or (b*n, 3*kpad) bf16 rows. */
 int pn2_pack_rows_split_bf16(int b, int c, int n, int kpad, int terms, const float* features, void* out,
                              void* stream);
 
@@ -308,7 +315,7 @@ int pn2_bn_bwd_stats(long long rows, int c, int ld_da, int ld_y, const float* da
 
 /* dy = gamma * invstd * (dYhat - (s1 + xhat * s2) / count)  (count > 0: batch statistics) or
  * gamma * invstd * dYhat  (count == 0: frozen statistics) -> operand rows in the `terms` layout of
- * pn2_bn_relu_rows: (rows, c), (rows, 3c) or (rows, 6c) bf16. */
+ * pn2_bn_relu_rows: (rows, c), (rows, 2c) or (rows, 3c) bf16. */
 int pn2_bn_bwd_rows(long long rows, int c, int ld_da, int ld_y, const float* da, const float* dout_pm,
                     const int* argmax, int ns, int npoint, const float* y, const float* scale,
                     const float* shift, const float* mean, const float* invstd, const float* gamma,
@@ -323,10 +330,10 @@ int pn2_wgrad_bf16(long long rows, int c_out, int c_in, int ld_dy, int ld_x, con
                    const void* x_bf16, float* dw, void* stream);
 
 /* The same contraction on split-precision operands in ONE launch: dy and x are rows in the `terms` layout of
- * pn2_bn_relu_rows / pn2_bn_bwd_rows (terms = 1: [h]; 2: [h|m|h]; 3: [h|m|h|l|h|m]; dy blocks c_out wide, x blocks
- * ld_x / {1, 3, 6} wide).  Every term of both operands is read once per 64-row chunk and all leading
- * (dy term, x term) products -- 1, 3 or 6 -- accumulate into one TMEM tile: against one pn2_wgrad_bf16 call per
- * product, half the operand traffic and a sixth of the launches / fp32 atomics at terms = 3. */
+ * pn2_bn_relu_rows / pn2_bn_bwd_rows ([h], [h|m], [h|m|l]; dy blocks c_out wide, x blocks ld_x / terms wide).
+ * Every term of both operands is read once per 64-row chunk and all leading (dy term, x term) products -- 1, 3
+ * or 6 -- accumulate into one TMEM tile: against one pn2_wgrad_bf16 call per product, half the operand traffic and
+ * a sixth of the launches / fp32 atomics at terms = 3. */
 int pn2_wgrad_split_bf16(long long rows, int c_out, int c_in, int ld_dy, int ld_x, const void* dy_bf16,
                          const void* x_bf16, int terms, float* dw, void* stream);
 

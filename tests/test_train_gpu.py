@@ -218,13 +218,13 @@ def test_backbone_train_step_vs_reference_golden(pkg, gold, cuda):
 
 
 def _split_rows(a, terms):
-    """fp32 (rows, c) -> bf16 rows in the `terms` layout of the training kernels: [h], [h|m|h], [h|m|h|l|h|m]."""
+    """fp32 (rows, c) -> bf16 rows in the `terms` layout of the training kernels: [h], [h|m], [h|m|l]."""
     h = a.bfloat16()
     r1 = a - h.float()
     m = r1.bfloat16()
     lo = (r1 - m.float()).bfloat16()
     t = (h, m, lo)
-    order = {1: (0,), 2: (0, 1, 0), 3: (0, 1, 0, 2, 0, 1)}[terms]
+    order = tuple(range(terms))
     return torch.cat([t[i] for i in order], dim=1).contiguous(), t
 
 
@@ -245,14 +245,14 @@ def test_wgrad_split_one_launch(pkg, cuda, terms, rows, c_out, c_in):
     x, xt = _split_rows(x32, terms)
     prods = {1: [(0, 0)], 2: [(0, 0), (1, 0), (0, 1)], 3: [(0, 0), (1, 0), (0, 1), (2, 0), (0, 2), (1, 1)]}[terms]
     want = sum(dyt[i].double().t() @ xt[j].double()[:, :c_in] for i, j in prods)
-    nblk = {1: 1, 2: 3, 3: 6}[terms]
+    nblk = terms
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     dw = torch.zeros(c_out, c_in, device=cuda)
     L.call("pn2_wgrad_split_bf16", ctypes.c_longlong(rows), c_out, c_in, nblk * c_out, nblk * kx, L.ptr(dy), L.ptr(x),
            terms, L.ptr(dw), st, device=cuda)
     scale = float(want.abs().max())
     assert float((dw.double() - want).abs().max()) <= 2e-5 * scale
-    first = {0: 0, 1: 1, 2: 3}
+    first = {0: 0, 1: 1, 2: 2}
     dw6 = torch.zeros(c_out, c_in, device=cuda)
     for i, j in prods:
         L.call("pn2_wgrad_bf16", ctypes.c_longlong(rows), c_out, c_in, nblk * c_out, nblk * kx,
