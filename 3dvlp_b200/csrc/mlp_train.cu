@@ -13,7 +13,7 @@
 //   backward, per layer  pn2_bn_bwd_stats      s1 = sum dYhat, s2 = sum dYhat xhat  (dYhat = upstream masked by ReLU;
 //                                              the last layer's upstream is the pooled gradient at the arg-max slot)
 //                        pn2_bn_bwd_rows       dY = gamma invstd (dYhat - s1/P - xhat s2/P)  -> bf16 rows
-//                        pn2_wgrad_bf16        dW = dY^T X on tcgen05: operands are transposed on the way into
+//                        pn2_wgrad_bf16        dW = dY^T X on tcgen05: MN-major operands, rows copied as they are into
 //                                              shared memory, split over K = P across persistent CTAs
 //                        pn2_linear_bf16       dX = dY W (the same linear kernel, W^T packed as its weight)
 //   pn2_unpack_rows      (P, ld) fp32 rows -> the reference's (B, C, n) layout (gradient w.r.t. the grouped tensor)
@@ -258,9 +258,15 @@ unpack_rows_kernel(int c, int n, int ld, long long bstride, const float* __restr
 }
 
 // ---- weight gradient: dW[co][ci] += sum_p dY[p][co] * X[p][ci] on tcgen05 -----------------------------
-// Both operands arrive as point-major rows, i.e. with the contraction index p as the SLOW dimension; the MMA
-// wants K-major tiles.  A thread loads 8 channels of two consecutive positions (two 16-byte loads), pairs them
-// per channel and writes eight 32-bit words into the SWIZZLE_128B K-major image (row = channel, k = position).
+// Both operands arrive as point-major rows, i.e. with the contraction index p as the SLOW dimension and the
+// channels contiguous: exactly the MN-MAJOR operand form of tcgen05.mma (instruction-descriptor bits a_major /
+// b_major = 1).  A 64-position x 64-channel panel of either operand is copied row by row with 16-byte cp.async
+// into the SWIZZLE_128B image (row = position, 128 bytes = 64 channels, chunk ^= row & 7) -- no transposition by
+// the threads (round 2 first wrote K-major tiles through eight 4-byte shared-memory stores per 16-byte load; that
+// store storm, not HBM, bounded the kernel).  Canonical MN-major SW128 layout (cute/atom/mma_traits_sm100.hpp):
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -- 64 channels contiguous, the next 64-channel panel LBO bytes
+// on, eight positions 128 bytes apart, the next eight SBO = 1024 bytes on; one MMA (K = 16 positions) advances
+// the start address by 2048 bytes.
 // CTA = one [128 x NT] block of dW (A rows = 128 output channels, zero rows beyond c_out) over a slice of P;
 // 64 positions per step, two shared-memory stages, accumulator in TMEM, fp32 atomics into dW at the end.
 constexpr int WG_THREADS = 128;
@@ -282,35 +288,16 @@ struct WgArgs {
 __device__ __constant__ int kWgProdDy[6] = {0, 1, 0, 2, 0, 1};
 __device__ __constant__ int kWgProdX[6] = {0, 0, 1, 0, 2, 1};
 
-__device__ __forceinline__ void wg_store_tile(uint32_t smem_tile, const __nv_bfloat16* __restrict__ src, int ld,
-                                              long long row0, long long rows, int ch0, int ch_count, int tile_rows,
-                                              int tid) {
-  // tile_rows channels x 64 positions; items = (position pair, 8-channel group).  A warp covers 16 position
-  // pairs x 2 adjacent channel groups: every 16-byte load is half of a fully used 32-byte sector, and the
-  // shared-memory words of lanes with different position pairs fall into different banks (the bank is a function
-  // of k = 2 pp under the 128-byte swizzle), leaving a 2-way conflict between the two channel groups.
-  const int groups = tile_rows >> 3;  // even: tile_rows is a multiple of 16
-  for (int it = tid; it < 32 * groups; it += WG_THREADS) {
-    const int pp = (it >> 1) & 31, cg = ((it >> 6) << 1) | (it & 1);
-    const long long p = row0 + 2 * pp;
-    const int c = ch0 + cg * 8;
-    uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
-    if (cg * 8 < ch_count) {  // ch_count is a multiple of 8
-      if (p < rows) lo = __ldg(reinterpret_cast<const uint4*>(src + p * ld + c));
-      if (p + 1 < rows) hi = __ldg(reinterpret_cast<const uint4*>(src + (p + 1) * ld + c));
-    }
-    const uint32_t l[4] = {lo.x, lo.y, lo.z, lo.w}, h[4] = {hi.x, hi.y, hi.z, hi.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      // channels 2e, 2e+1 of the group: word = (value at p) | (value at p+1) << 16
-      const uint32_t w0 = (l[e] & 0xffffu) | (h[e] << 16);
-      const uint32_t w1 = (l[e] >> 16) | (h[e] & 0xffff0000u);
-      const uint32_t r0 = cg * 8 + 2 * e, r1 = r0 + 1;
-      const uint32_t k = 2 * pp;  // even: 4-byte aligned inside its 16-byte chunk
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_tile + tc::swz_off(r0, k >> 3) + (k & 7) * 2), "r"(w0) : "memory");
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_tile + tc::swz_off(r1, k >> 3) + (k & 7) * 2), "r"(w1) : "memory");
-    }
-  }
+// 64-bit shared-memory descriptor of an MN-major SWIZZLE_128B operand: panels of 64 channels 8 KB apart (LBO),
+// groups of eight positions 1 KB apart (SBO)
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(8192 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
 }
 
 __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgArgs a) {
@@ -319,12 +306,13 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgArgs a) {
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_bytes = 128u * 128u, b_bytes = (static_cast<uint32_t>(a.nt) * 128u + 1023u) & ~1023u;
+  // a.nt is a multiple of 64 here: whole 64-channel panels of 64 positions x 128 bytes = 8 KB
+  const uint32_t a_bytes = 2u * 8192u, b_bytes = static_cast<uint32_t>(a.nt >> 6) * 8192u;
   const uint32_t stage_bytes = static_cast<uint32_t>(a.terms) * (a_bytes + b_bytes);  // terms A tiles, then terms B tiles
   const int n_prod = a.terms == 1 ? 1 : (a.terms == 2 ? 3 : 6);
   const int co0 = blockIdx.y * 128, ci0 = blockIdx.z * a.nt;  // nz > 1 only with full nt-wide tiles
   const int co_cnt = min(128, a.c_out - co0);                 // multiple of 8
-  const int ci_cnt = min(a.nt, ((a.c_in - ci0) + 7) & ~7);      // channels with data (x rows are padded to ld_x)
+  const int ci_cnt = min(a.nt, ((a.c_in - ci0) + 7) & ~7);      // channels with data (x blocks are padded to 8)
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(a.nt)) tmem_cols <<= 1;
   if (tid == 0) {
@@ -336,36 +324,64 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgArgs a) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_d = tmem_slot;
-  const uint32_t idesc = tc::idesc_bf16_f32(128, a.nt);
+  // M = 128, N = nt, both operands MN-major (bits 15 / 16)
+  const uint32_t idesc = tc::idesc_bf16_f32(128, a.nt) | (1u << 15) | (1u << 16);
   const long long total_chunks = (a.rows + 63) / 64;
   const long long c_first = static_cast<long long>(blockIdx.x) * a.chunks_per_cta;
   long long c_last = c_first + a.chunks_per_cta;
   if (c_last > total_chunks) c_last = total_chunks;
+  const int n_chunks = c_last > c_first ? static_cast<int>(c_last - c_first) : 0;
+  const int b_chunks = a.nt >> 3;  // 16-byte chunks per position of a B tile
+
+  // every term of both operands is read ONCE per chunk of 64 positions
+  auto load = [&](int i, int s) {
+    const long long row0 = (c_first + i) * 64;
+    const uint32_t sa = base + s * stage_bytes, sb = sa + static_cast<uint32_t>(a.terms) * a_bytes;
+    for (int t = 0; t < a.terms; ++t) {
+      const __nv_bfloat16* dy_t = a.dy + t * a.blk_dy + co0;
+      const __nv_bfloat16* x_t = a.x + t * a.blk_x + ci0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {  // A: 64 positions x 16 chunks
+        const int q = u * WG_THREADS + tid, k = q >> 4, j = q & 15;
+        const bool ok = row0 + k < a.rows && j * 8 < co_cnt;
+        const __nv_bfloat16* src = ok ? dy_t + (row0 + k) * a.ld_dy + j * 8 : a.dy;
+        tc::cp_async16(sa + t * a_bytes + (j >> 3) * 8192u + tc::swz_off(k, j & 7), src, ok);
+      }
+      for (int q = tid; q < 64 * b_chunks; q += WG_THREADS) {  // B: 64 positions x nt / 8 chunks
+        const int k = q / b_chunks, j = q - k * b_chunks;
+        const bool ok = row0 + k < a.rows && j * 8 < ci_cnt;
+        const __nv_bfloat16* src = ok ? x_t + (row0 + k) * a.ld_x + j * 8 : a.x;
+        tc::cp_async16(sb + t * b_bytes + (j >> 3) * 8192u + tc::swz_off(k, j & 7), src, ok);
+      }
+    }
+    tc::cp_async_commit();
+  };
+
   bool failed = false;
   int n_issued = 0;
-  for (long long ck = c_first; ck < c_last && !failed; ++ck, ++n_issued) {
-    const int s = n_issued & 1;
-    // stage s was last read by the MMAs issued two steps ago
-    if (n_issued >= 2 && !mbar_wait(&bar_mma[s], ((n_issued - 2) >> 1) & 1)) { failed = true; break; }
-    const uint32_t sa = base + s * stage_bytes;
-    const uint32_t sb = sa + static_cast<uint32_t>(a.terms) * a_bytes;
-    // every term of both operands is read ONCE per chunk (one launch per product read each of them up to three times)
-    for (int t = 0; t < a.terms; ++t) {
-      const int blk = t;
-      wg_store_tile(sa + t * a_bytes, a.dy + blk * a.blk_dy, a.ld_dy, ck * 64, a.rows, co0, co_cnt, 128, tid);
-      wg_store_tile(sb + t * b_bytes, a.x + blk * a.blk_x, a.ld_x, ck * 64, a.rows, ci0, ci_cnt, a.nt, tid);
+  if (n_chunks > 0) load(0, 0);
+  for (int i = 0; i < n_chunks; ++i, ++n_issued) {
+    const int s = i & 1;
+    if (i + 1 < n_chunks) {
+      // stage s^1 was last read by the MMAs of chunk i-1
+      if (i >= 1 && !mbar_wait(&bar_mma[s ^ 1], ((i - 1) >> 1) & 1)) { failed = true; break; }
+      load(i + 1, s ^ 1);
+      tc::cp_async_wait<1>();
+    } else {
+      tc::cp_async_wait<0>();
     }
     fence_proxy_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     if (tid == 0) {
       tc::fence_after_sync();
+      const uint32_t sa = base + s * stage_bytes, sb = sa + static_cast<uint32_t>(a.terms) * a_bytes;
       for (int pr = 0; pr < n_prod; ++pr) {
         const uint32_t ta = sa + kWgProdDy[pr] * a_bytes, tb = sb + kWgProdX[pr] * b_bytes;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          tc::mma_bf16(tmem_d, tc::smem_desc_sw128(ta + kk * 32), tc::smem_desc_sw128(tb + kk * 32), idesc,
-                       (n_issued > 0 || pr > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk)  // 16 positions per MMA = two 1 KB groups of eight
+          tc::mma_bf16(tmem_d, smem_desc_mn_sw128(ta + kk * 2048), smem_desc_mn_sw128(tb + kk * 2048), idesc,
+                       (i > 0 || pr > 0 || kk > 0) ? 1u : 0u);
       }
       tc::mma_commit(&bar_mma[s]);
     }
@@ -541,7 +557,7 @@ static int wgrad_launch(long long rows, int c_out, int c_in, int ld_dy, int ld_x
   PN2_REQUIRE(a.err != nullptr, "%s: cannot allocate the device error flag", who);
   // N tile: up to 256 input channels, 128 with three terms (two stages of 3 x (16 + 16) KB must fit shared memory)
   const int nt_max = terms == 3 ? 128 : 256;
-  const int nt = c_in >= nt_max ? nt_max : ((c_in + 15) & ~15);
+  const int nt = c_in >= nt_max ? nt_max : ((c_in + 63) & ~63);  // whole 64-channel MN-major panels
   const int nz = (c_in + nt - 1) / nt, ny = (c_out + 127) / 128;
   a.nt = nt;
   const long long chunks = (rows + 63) / 64;
@@ -550,7 +566,7 @@ static int wgrad_launch(long long rows, int c_out, int c_in, int ld_dy, int ld_x
   if (ctas > chunks) ctas = chunks;
   a.chunks_per_cta = (chunks + ctas - 1) / ctas;
   ctas = (chunks + a.chunks_per_cta - 1) / a.chunks_per_cta;
-  const size_t stage = static_cast<size_t>(terms) * (128 * 128 + ((static_cast<size_t>(nt) * 128 + 1023) & ~static_cast<size_t>(1023)));
+  const size_t stage = static_cast<size_t>(terms) * (2 * 8192 + static_cast<size_t>(nt / 64) * 8192);
   const size_t smem = 2 * stage + 1024;
   PN2_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>(ctas), ny, nz);

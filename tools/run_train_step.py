@@ -38,6 +38,39 @@ def step():
 for _ in range(2):
     step()
 torch.cuda.synchronize()
+# host-side phases, each closed by a device synchronisation (so the sum exceeds the pipelined step)
+import time
+def phase_times():
+    t = {}
+    def tick(name, t0):
+        torch.cuda.synchronize(); t[name] = (time.perf_counter() - t0) * 1e3; return time.perf_counter()
+    t0 = time.perf_counter()
+    opt.zero_grad(set_to_none=True)
+    d = det({"point_clouds": pc}); t0 = tick("forward (detector)", t0)
+    d.update(labels); d.update({"epoch": 10, "istrain": 1, "random": 0.7, "cluster_ref": cluster_ref})
+    d = LD.get_detection_loss(d, cfg); d, ref_loss, _, _ = LG.compute_diou_loss(d, cfg)
+    loss = d["vote_loss"] + 0.1 * d["objectness_loss"] + d["box_loss"] + 0.3 * ref_loss + d["diou_loss"]; t0 = tick("losses", t0)
+    loss.backward(); t0 = tick("backward", t0)
+    opt.step(); t0 = tick("optimizer", t0)
+    return t
+pt = phase_times(); pt = phase_times()
+print("phases (ms, each synchronised):", {k: round(v, 2) for k, v in pt.items()})
+# the same phases WITHOUT synchronisation: host issue time only
+def issue_times():
+    t = {}
+    t0 = time.perf_counter()
+    opt.zero_grad(set_to_none=True)
+    d = det({"point_clouds": pc}); t["forward (detector)"] = (time.perf_counter() - t0) * 1e3; t0 = time.perf_counter()
+    d.update(labels); d.update({"epoch": 10, "istrain": 1, "random": 0.7, "cluster_ref": cluster_ref})
+    d = LD.get_detection_loss(d, cfg); d, ref_loss, _, _ = LG.compute_diou_loss(d, cfg)
+    loss = d["vote_loss"] + 0.1 * d["objectness_loss"] + d["box_loss"] + 0.3 * ref_loss + d["diou_loss"]
+    t["losses"] = (time.perf_counter() - t0) * 1e3; t0 = time.perf_counter()
+    loss.backward(); t["backward"] = (time.perf_counter() - t0) * 1e3; t0 = time.perf_counter()
+    opt.step(); t["optimizer"] = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
+    return t
+it = issue_times(); it = issue_times()
+print("host issue time per phase (ms):", {k: round(v, 2) for k, v in it.items()})
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(steps):
