@@ -19,14 +19,14 @@ from ._lib import get_option, get_stat, set_option, set_option_thread, thread_op
 from . import _ext, backbone, mlp_train, nn_distance as _nn_distance_mod, pointnet2_modules, pointnet2_utils, pytorch_utils, voting, loss_detection, box_util, loss_grounding, contrast, proposal  # noqa: F401
 from .backbone import Pointnet2Backbone  # noqa: F401
 from .mlp_train import mlp_backend  # noqa: F401
-from .graph import GraphedBackbone  # noqa: F401
+from .graph import GraphedBackbone, GraphedTrainStep  # noqa: F401
 from .nn_distance import huber_loss, knn_distance, nn_distance  # noqa: F401
 from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes  # noqa: F401
 from .voting import VoteNetFrontEnd, VotingModule  # noqa: F401
 from .contrast import ContrastModule  # noqa: F401
 from .proposal import ProposalModule, StandardROIHeads, VoteNetDetector  # noqa: F401
 
-__all__ = ["Pointnet2Backbone", "GraphedBackbone", "VotingModule", "VoteNetFrontEnd", "ProposalModule", "StandardROIHeads", "VoteNetDetector", "PointnetSAModuleVotes", "PointnetFPModule", "nn_distance", "huber_loss",
+__all__ = ["Pointnet2Backbone", "GraphedBackbone", "GraphedTrainStep", "VotingModule", "VoteNetFrontEnd", "ProposalModule", "StandardROIHeads", "VoteNetDetector", "PointnetSAModuleVotes", "PointnetFPModule", "nn_distance", "huber_loss",
            "knn_distance", "pointnet2_utils", "pointnet2_modules", "pytorch_utils", "install_dropin"]
 
 

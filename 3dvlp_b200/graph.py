@@ -1,4 +1,5 @@
-"""CUDA-graph replay of the eval-mode backbone.
+"""CUDA-graph replay of the eval-mode backbone (GraphedBackbone) and of a whole training step
+(GraphedTrainStep).
 
 A backbone forward is ~40 short kernel launches on two streams; at 2 ms per step the Python / driver
 launch path is of the same order as the GPU work.  Shapes are static (B scenes x N points), every
@@ -112,3 +113,53 @@ class GraphedBackbone:
                 return self.backbone({"point_clouds": self.static_in})
         self.graph.replay()
         return self.static_out
+
+
+class GraphedTrainStep:
+    """A whole training iteration -- forward in train() mode, losses, backward, optimizer step -- captured ONCE
+    as a CUDA graph and replayed with one launch per iteration.
+
+    The reference's training loop (``lib/joint/solver_3dvlp.py:580-584``: forward, loss, ``backward()``,
+    ``optimizer.step()``) issues ~3 900 kernels per iteration at this path's sizes; on a B200 their device time
+    is shorter than the time the host needs to launch them.  Every kernel of this library is stream-ordered
+    (workspaces come from the stream-ordered allocator, the loss glue has no host synchronisation), so the
+    iteration is capturable as it is.
+
+    ``loss_fn()`` runs forward + losses on STATIC input tensors it closes over and returns the scalar loss;
+    ``optimizer`` must be capturable (``torch.optim.Adam(..., capturable=True)``).  ``step()`` replays the graph
+    and returns the static loss tensor (overwritten by the next replay); new data is fed by ``copy_``-ing it
+    into the static inputs first.  BatchNorm running statistics, parameters and optimizer state are updated in
+    place by the replay exactly as by an eager iteration.
+    """
+
+    def __init__(self, loss_fn, optimizer, warmup=3):
+        for grp in optimizer.param_groups:
+            if "capturable" in grp and not grp["capturable"]:
+                raise RuntimeError("GraphedTrainStep needs a capturable optimizer (e.g. Adam(..., capturable=True))")
+        self.loss_fn, self.optimizer = loss_fn, optimizer
+        cur = torch.cuda.current_stream()
+        s = torch.cuda.Stream()
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            for _ in range(max(1, warmup)):  # host-side caches, lazily created optimizer state, allocator pools
+                self._eager()
+        cur.wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)  # gradients are (re)created inside the graph's private pool
+        with torch.cuda.graph(self.graph):
+            loss = loss_fn()
+            loss.backward()
+            optimizer.step()
+            self.loss = loss.detach()
+
+    def _eager(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.loss_fn()
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def step(self):
+        self.graph.replay()
+        return self.loss

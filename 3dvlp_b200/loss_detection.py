@@ -61,10 +61,22 @@ def compute_objectness_loss(data_dict):
     objectness_mask = (near | (euclidean_dist1 > FAR_THRESHOLD)).float()
 
     objectness_scores = data_dict['objectness_scores']
-    weight = torch.tensor(OBJECTNESS_CLS_WEIGHTS, device=objectness_scores.device, dtype=objectness_scores.dtype)
+    weight = _objectness_weights(objectness_scores.device, objectness_scores.dtype)
     loss = F.cross_entropy(objectness_scores.transpose(2, 1), objectness_label, weight=weight, reduction='none')
     objectness_loss = torch.sum(loss * objectness_mask) / (torch.sum(objectness_mask) + 1e-6)
     return objectness_loss, objectness_label, objectness_mask, ind1
+
+
+_WEIGHT_CACHE = {}
+
+
+def _objectness_weights(device, dtype):
+    """The class weights as a device constant, uploaded once per (device, dtype): a host -> device copy per
+    call would also make the loss uncapturable in a CUDA graph (graph.GraphedTrainStep)."""
+    w = _WEIGHT_CACHE.get((device, dtype))
+    if w is None:
+        w = _WEIGHT_CACHE[(device, dtype)] = torch.tensor(OBJECTNESS_CLS_WEIGHTS, device=device, dtype=dtype)
+    return w
 
 
 def compute_box_loss(data_dict, config, distance_huber_loss_thres=0.15, use_centerness=False):

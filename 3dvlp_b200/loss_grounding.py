@@ -76,8 +76,10 @@ def compute_diou_loss(data_dict, config, no_reference=False, use_reg_head=False,
         # `istrain` may be a device tensor: folded into a select instead of read back
         istrain = data_dict["istrain"]
         istrain = istrain[0] if torch.is_tensor(istrain) or isinstance(istrain, (list, tuple)) else istrain
-        train = torch.as_tensor(istrain, device=dev) == 1
-        ious = torch.where(train, ious * objectness_masks[:, None, :], ious)
+        if torch.is_tensor(istrain):
+            ious = torch.where(istrain.to(dev) == 1, ious * objectness_masks[:, None, :], ious)
+        elif istrain == 1:  # a host value: decided on the host, nothing uploaded (capturable in a CUDA graph)
+            ious = ious * objectness_masks[:, None, :]
 
     ind_np = ious_np.argmax(-1)                                            # (B,L)
     max_ious = ious_np.gather(-1, ind_np.unsqueeze(-1)).squeeze(-1)

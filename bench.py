@@ -17,13 +17,13 @@ A "step" is one eval-mode forward of the backbone over one batch of 8 scenes per
                timed on this box's host cores on a bounded sample (rank 0, N = 1 only)
 """
 import argparse
+import gc
 import importlib
 import json
 import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -48,14 +48,15 @@ class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML
     (nvidia_ml_py).  Spawning `nvidia-smi -lms` instead was measured to stall CUDA-graph launches for
     milliseconds at a time (its start-up and every poll take driver-wide locks): an intermittent 2x
-    loss on a step that is one graph launch per 0.45 ms.  Falls back to one nvidia-smi query after the
-    region if NVML is unavailable."""
-
-    PERIOD_S = 0.025
+    loss on a step that is one graph launch per 0.3 ms.  In-process NVML queries go through the same
+    driver, so they are not issued from a background thread either: the main thread samples AFTER it has
+    enqueued the region's K steps and BEFORE the closing synchronisation -- the GPU is still working
+    through the region (checked with the closing event's query()), but no launch is left to be delayed.
+    Falls back to one nvidia-smi query after the region if NVML is unavailable."""
 
     def __init__(self, index):
-        self.index, self.rows, self.first, self.t, self.nv, self.h = index, [], 0, None, None, None
-        self.running = False
+        self.index, self.rows, self.nv, self.h = index, [], None, None
+        self.in_region = 0
 
     def start(self):
         try:
@@ -66,42 +67,39 @@ class ClockSampler:
             phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
             self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.running = True
-            self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
+            self._sample()  # first use of the NVML entry points happens outside the timed region
+            self.rows = []
         except Exception:
             self.nv = None
 
-    def _poll(self):
+    def _sample(self):
         nv = self.nv
-        while self.running:
-            try:
-                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.rows.append((mhz, mask))
-            except Exception:
-                pass
-            time.sleep(self.PERIOD_S)
+        mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        self.rows.append((mhz, mask))
 
-    def wait_ready(self, timeout=5.0):
-        t0 = time.time()
-        while self.nv is not None and not self.rows and time.time() - t0 < timeout:
-            time.sleep(0.01)
-
-    def mark(self):
-        """Samples from here on belong to the timed region."""
-        self.first = len(self.rows)
+    def sample_until(self, end_event, period_s=0.002, max_samples=200):
+        """Called between the last enqueue and the closing synchronisation: sample while `end_event` (recorded
+        after the K steps) is still pending, i.e. while the GPU is inside the timed region."""
+        if self.nv is None:
+            return
+        try:
+            while len(self.rows) < max_samples:
+                self._sample()
+                if end_event.query():  # the region was over when (or just after) this sample was taken
+                    break
+                self.in_region += 1
+                time.sleep(period_s)
+        except Exception:
+            pass
 
     def stop(self):
         if self.nv is None:
             return self._one_shot()
-        time.sleep(self.PERIOD_S * 1.5)
-        self.running = False
-        self.t.join(timeout=1.0)
-        rows = self.rows[self.first:] or self.rows[-1:]
+        rows = self.rows
         nv = self.nv
         names = (("hw_slowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
                  ("hw_thermal_slowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
@@ -110,7 +108,8 @@ class ClockSampler:
         reasons = sorted({n for _, mask in rows for n, bit in names if mask & bit})
         sm = [r[0] for r in rows]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                "samples": len(sm), "source": "nvml"}
+                "samples": len(sm), "samples_before_region_end": self.in_region,
+                "source": "nvml, main thread, after the last enqueue of the timed region and before its closing sync"}
 
     def _one_shot(self):
         try:
@@ -395,20 +394,23 @@ def train_step_leg(torch, dist, pkg, syn, dev, host_pool, world, rank, steps=5):
     det = pkg.VoteNetDetector(input_feature_dim=C_IN, mean_size_arr=msa).to(dev).train()
     cfg = types.SimpleNamespace(num_class=18, num_heading_bin=1, num_size_cluster=18, mean_size_arr=msa,
                                 mean_size_arr_tensor=torch.from_numpy(msa).to(dev))
-    opt = torch.optim.Adam(det.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(det.parameters(), lr=1e-3, capturable=True)
     pc = host_pool[0].to(dev)
     labels = {k: v.to(dev) for k, v in syn.make_labels(host_pool[0], seed=100 + rank, lang_num_max=8).items()}
     g = torch.Generator().manual_seed(300 + rank)
     cluster_ref = torch.randn(SCENES_PER_GPU * 8, 256, generator=g).to(dev)
 
-    def step():
-        opt.zero_grad(set_to_none=True)
+    def loss_fn():
         d = det({"point_clouds": pc})
         d.update(labels)
         d.update({"epoch": 10, "istrain": 1, "random": 0.7, "cluster_ref": cluster_ref})
         d = LD.get_detection_loss(d, cfg)
         d, ref_loss, _, _ = LG.compute_diou_loss(d, cfg)
-        loss = d["vote_loss"] + 0.1 * d["objectness_loss"] + d["box_loss"] + 0.3 * ref_loss + d["diou_loss"]
+        return d["vote_loss"] + 0.1 * d["objectness_loss"] + d["box_loss"] + 0.3 * ref_loss + d["diou_loss"]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn()
         loss.backward()
         opt.step()
         return loss.detach()
@@ -433,9 +435,34 @@ def train_step_leg(torch, dist, pkg, syn, dev, host_pool, world, rank, steps=5):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
     mlp = importlib.import_module("3dvlp_b200.mlp_train")
+    # the same iteration captured ONCE as a CUDA graph (graph.GraphedTrainStep): ~3 900 launches become one, the
+    # step is bound by its kernels instead of by the host's launch rate
+    graphed = None
+    try:
+        gs = pkg.GraphedTrainStep(loss_fn, opt, warmup=1)
+        for _ in range(2):
+            gs.step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        for _ in range(steps):
+            gloss = gs.step()
+        e1.record()
+        torch.cuda.synchronize()
+        gms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([gms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            gms = float(t[0])
+        graphed = {"value": SCENES_PER_GPU * world / (gms * 1e-3), "ms_per_step": gms, "loss_last_rank0": float(gloss),
+                   "what": "the same iteration replayed as one CUDA graph (GraphedTrainStep)"}
+    except Exception as ex:  # capture depends on the driver / torch build: the eager figure stands
+        graphed = {"unavailable": repr(ex)[:200]}
+        torch.cuda.synchronize()
     return {"value": SCENES_PER_GPU * world / (ms * 1e-3), "unit": "scenes/s", "ms_per_step": ms, "steps": steps,
             "loss_first_last_rank0": [losses[0], losses[-1]], "operand_precision": mlp._PRECISION[0],
-            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30, "graphed": graphed,
             "what": "TRAINING step of BASELINE configs[2]: detector forward in train() mode + detection / DIoU losses + "
                     "backward + Adam, eager, 8 scenes x 40000 pts per GPU; shared MLPs forward and backward on own "
                     "tcgen05 kernels"}
@@ -577,7 +604,6 @@ def main():
     # ---------------- device-resident throughput --------------------------------------------------
     clocks = ClockSampler(local_rank)
     clocks.start()
-    clocks.wait_ready()
     # Untimed settling before the W warm-up steps: the first few hundred graph launches of a process are
     # occasionally issued at ~1 ms each (driver-side first-use work; measured with
     # tools/throughput_stability.py), which W = 3..24 steps do not cover.  Chunks of 100 steps until two
@@ -593,11 +619,17 @@ def main():
         prev = dt
     run_steps(0, args.warmup, lambda g, s: g(dev_pool[s % POOL]))
     barrier()
-    clocks.mark()
+    # a cyclic garbage collection inside a 6 ms timed region (K = 20) would be a visible share of it: the heap
+    # is collected now and the collector paused until both timed regions are over
+    gc.collect()
+    gc.disable()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_issue = time.perf_counter()
     run_steps(args.warmup, args.steps, lambda g, s: g(dev_pool[s % POOL]))
     e1.record()
+    host_issue_ms = (time.perf_counter() - t_issue) * 1e3
+    clocks.sample_until(e1)
     barrier()
     ms = e0.elapsed_time(e1)
     launches = launches_per_step * args.steps
@@ -626,10 +658,14 @@ def main():
     run_steps(0, args.warmup, e2e_step, e_graphs, e_lanes)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gc.collect()
     f0.record()
+    t_issue = time.perf_counter()
     run_steps(args.warmup, args.steps, e2e_step, e_graphs, e_lanes)
     f1.record()
+    host_issue_ms_e2e = (time.perf_counter() - t_issue) * 1e3
     barrier()
+    gc.enable()
     ms_e2e = f0.elapsed_time(f1)
     graphs[0].check()  # raises if any kernel bailed out of a bounded wait during the timed regions
     h2d = dev_pool[0].numel() * 4
@@ -728,7 +764,9 @@ def main():
                     "e2e_lane_priority_levels": levels, "e2e_host_calls_per_step": 3, "numa": numa,
                     "fps_algorithm": "bucketed single-SM (throughput mode)" if throughput_mode else "16-CTA cluster (latency mode)"},
                 "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                        "host_issue_ms": round(host_issue_ms_e2e, 3)},
+                "host_issue_ms": round(host_issue_ms, 3),  # wall time the host spent enqueueing the K steps (rank 0)
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_ops": roofline_ops[:24],
                 "roofline_ops_note": "per C-ABI call, timed alone (eager, CUDA events, median of 5) under the options the "
                                      "timed graphs captured (%s); shares are of the SERIALISED per-op sum, not of the "

@@ -259,3 +259,70 @@ def test_wgrad_split_one_launch(pkg, cuda, terms, rows, c_out, c_in):
                ctypes.c_void_p(dy.data_ptr() + 2 * first[i] * c_out), ctypes.c_void_p(x.data_ptr() + 2 * first[j] * kx),
                L.ptr(dw6), st, device=cuda)
     assert float((dw - dw6).abs().max()) <= 2e-5 * scale
+
+
+def test_graphed_train_step_matches_eager(pkg, cuda):
+    """graph.GraphedTrainStep: the whole training iteration of the detector (train-mode forward on the tcgen05
+    training path, detection + DIoU losses, backward, Adam) captured as ONE CUDA graph.  From the same model /
+    optimizer state a replay and an eager iteration must produce the same loss, gradients, running statistics
+    and updated parameters (up to the order of the fp32 atomics of the scatter-add / weight gradients)."""
+    import types
+    syn = importlib.import_module("3dvlp_b200.synthetic")
+    LD = importlib.import_module("3dvlp_b200.loss_detection")
+    LG = importlib.import_module("3dvlp_b200.loss_grounding")
+    msa = syn.mean_size_arr()
+    cfg = types.SimpleNamespace(num_class=18, num_heading_bin=1, num_size_cluster=18, mean_size_arr=msa,
+                                mean_size_arr_tensor=torch.from_numpy(msa).to(cuda))
+    host = syn.make_batch(3, 2, 8000, 1)
+    pc = host.to(cuda)
+    labels = {k: v.to(cuda) for k, v in syn.make_labels(host, seed=7, lang_num_max=4).items()}
+    cluster_ref = torch.randn(2 * 4, 256, generator=torch.Generator().manual_seed(5)).to(cuda)
+    torch.manual_seed(11)
+    det = pkg.VoteNetDetector(input_feature_dim=1, mean_size_arr=msa).to(cuda).train()
+    opt = torch.optim.Adam(det.parameters(), lr=1e-3, capturable=True)
+
+    def loss_fn():
+        d = det({"point_clouds": pc})
+        d.update(labels)
+        d.update({"epoch": 10, "istrain": 1, "random": 0.7, "cluster_ref": cluster_ref})
+        d = LD.get_detection_loss(d, cfg)
+        d, ref_loss, _, _ = LG.compute_diou_loss(d, cfg)
+        return d["vote_loss"] + 0.1 * d["objectness_loss"] + d["box_loss"] + 0.3 * ref_loss + d["diou_loss"]
+
+    with pytest.raises(RuntimeError, match="capturable"):
+        pkg.GraphedTrainStep(loss_fn, torch.optim.Adam(det.parameters(), lr=1e-3))
+    g = pkg.GraphedTrainStep(loss_fn, opt, warmup=2)
+    params = dict(det.named_parameters())
+    state = [t for st in opt.state.values() for t in st.values() if torch.is_tensor(t)]
+    tensors = list(params.values()) + list(det.buffers()) + state
+    snap = [t.detach().clone() for t in tensors]
+
+    loss_g = g.step().clone()
+    grads_g = {n: p.grad.detach().clone() for n, p in params.items() if p.grad is not None}
+    after_g = [t.detach().clone() for t in tensors]
+    with torch.no_grad():
+        for t, s in zip(tensors, snap):
+            t.copy_(s)
+    loss = loss_fn()
+    names = [n for n in params if n in grads_g]
+    grads_e = dict(zip(names, torch.autograd.grad(loss, [params[n] for n in names], allow_unused=True)))
+    loss_e = float(loss.detach())
+    assert abs(loss_e - float(loss_g)) <= 1e-4 * abs(loss_e), (loss_e, float(loss_g))
+    assert len(grads_g) > 60  # backbone, voting and proposal parameters received a gradient inside the graph
+    worst = 0.0
+    for n in names:
+        if grads_e[n] is None:
+            continue
+        worst = max(worst, _rms_err(grads_g[n], grads_e[n].cpu().numpy()))
+    assert worst < 1e-3, worst
+    # the eager optimizer step from the restored state lands on the replay's parameters / statistics
+    for n in names:
+        params[n].grad = grads_e[n]
+    opt.step()
+    n_par = len(params)
+    for i, (t, a) in enumerate(zip(tensors, after_g)):
+        if i < n_par:  # Adam turns gradient noise of near-zero entries into +-lr steps: compare in units of lr
+            assert float((t.detach() - a).abs().max()) <= 2.5e-3, i
+        elif t.dtype.is_floating_point and i < n_par + len(list(det.buffers())):
+            np.testing.assert_allclose(t.cpu().numpy(), a.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    assert pkg.tensorcore.poll_device_error(cuda) == 0
