@@ -437,12 +437,18 @@ def train_step_leg(torch, dist, pkg, syn, dev, host_pool, world, rank, steps=5):
     mlp = importlib.import_module("3dvlp_b200.mlp_train")
     # the same iteration captured ONCE as a CUDA graph (graph.GraphedTrainStep): ~3 900 launches become one, the
     # step is bound by its kernels instead of by the host's launch rate
-    graphed = None
+    gs, why = None, ""
     try:
         gs = pkg.GraphedTrainStep(loss_fn, opt, warmup=1)
         for _ in range(2):
             gs.step()
-        torch.cuda.synchronize()
+    except Exception as ex:  # capture depends on the driver / torch build: the eager figure stands
+        gs, why = None, repr(ex)[:200]
+    torch.cuda.synchronize()
+    ok = torch.tensor([1.0 if gs is not None else 0.0], device=dev, dtype=torch.float64)
+    if world > 1:  # every rank replays or none does: the timed loop below contains collectives
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok[0]) > 0.5:
         if world > 1:
             dist.barrier()
         e0.record()
@@ -457,9 +463,8 @@ def train_step_leg(torch, dist, pkg, syn, dev, host_pool, world, rank, steps=5):
             gms = float(t[0])
         graphed = {"value": SCENES_PER_GPU * world / (gms * 1e-3), "ms_per_step": gms, "loss_last_rank0": float(gloss),
                    "what": "the same iteration replayed as one CUDA graph (GraphedTrainStep)"}
-    except Exception as ex:  # capture depends on the driver / torch build: the eager figure stands
-        graphed = {"unavailable": repr(ex)[:200]}
-        torch.cuda.synchronize()
+    else:
+        graphed = {"unavailable": why or "capture failed on another rank"}
     return {"value": SCENES_PER_GPU * world / (ms * 1e-3), "unit": "scenes/s", "ms_per_step": ms, "steps": steps,
             "loss_first_last_rank0": [losses[0], losses[-1]], "operand_precision": mlp._PRECISION[0],
             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30, "graphed": graphed,
