@@ -51,6 +51,62 @@ __device__ __forceinline__ void column_reduce2(long long rows, int c, long long 
   }
 }
 
+// The same reduction with thread = (row lane, FOUR channels): 16-byte loads, four rows in flight per thread.  A
+// thread's channels are fixed, so per-channel constants of the functor live in registers.  Needs c % 4 == 0 and
+// 16-byte aligned rows (checked by the callers, which fall back to the scalar kernels otherwise).
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+template <typename F>
+__device__ __forceinline__ void column_reduce2_v4(long long rows, int c, long long rows_per_cta, F f, double* o1, double* o2) {
+  __shared__ float4 s_a[RT], s_b[RT];
+  const int cq = c >> 2;                       // channel quads (cq <= RT / 4... <= RT)
+  const int lanes = RT / cq;
+  const int tx = threadIdx.x % cq, ty = threadIdx.x / cq;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (ty < lanes) {
+    long long r = r0 + ty;
+    for (; r + 3 * lanes < r1; r += 4 * lanes) {  // four rows in flight
+      float4 a0, b0, a1, b1, a2, b2, a3, b3;
+      f(r, a0, b0);
+      f(r + lanes, a1, b1);
+      f(r + 2 * lanes, a2, b2);
+      f(r + 3 * lanes, a3, b3);
+      a = f4_add(a, f4_add(f4_add(a0, a1), f4_add(a2, a3)));
+      b = f4_add(b, f4_add(f4_add(b0, b1), f4_add(b2, b3)));
+    }
+    for (; r < r1; r += lanes) {
+      float4 a0, b0;
+      f(r, a0, b0);
+      a = f4_add(a, a0);
+      b = f4_add(b, b0);
+    }
+  }
+  s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
+  __syncthreads();
+  if (ty == 0) {
+    double da[4] = {0.0, 0.0, 0.0, 0.0}, db[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int l = 0; l < lanes; ++l) {
+      const float4 va = s_a[l * cq + tx], vb = s_b[l * cq + tx];
+      da[0] += va.x; da[1] += va.y; da[2] += va.z; da[3] += va.w;
+      db[0] += vb.x; db[1] += vb.y; db[2] += vb.z; db[3] += vb.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { atomicAdd(o1 + 4 * tx + k, da[k]); atomicAdd(o2 + 4 * tx + k, db[k]); }
+  }
+}
+
+__global__ void __launch_bounds__(RT, 4)
+column_stats_v4_kernel(long long rows, int c, int ld, long long rows_per_cta, const float* __restrict__ y,
+                       double* __restrict__ sum, double* __restrict__ sumsq) {
+  const int ch0 = (threadIdx.x % (c >> 2)) << 2;
+  column_reduce2_v4(rows, c, rows_per_cta, [&](long long r, float4& a, float4& b) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(y + r * ld + ch0));
+    a = v; b = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+  }, sum, sumsq);
+}
+
 __global__ void __launch_bounds__(RT)
 column_stats_kernel(long long rows, int c, int ld, long long rows_per_cta, const float* __restrict__ y,
                     double* __restrict__ sum, double* __restrict__ sumsq) {
@@ -184,6 +240,24 @@ bn_bwd_stats_dense_kernel(long long rows, int c, int ld_da, int ld_y, long long 
   }, s1, s2);
 }
 
+__global__ void __launch_bounds__(RT, 4)
+bn_bwd_stats_dense_v4_kernel(long long rows, int c, int ld_da, int ld_y, long long rows_per_cta, const float* __restrict__ da,
+                             const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                             const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ s1,
+                             double* __restrict__ s2) {
+  const int ch0 = (threadIdx.x % (c >> 2)) << 2;
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + ch0)), sh = __ldg(reinterpret_cast<const float4*>(shift + ch0));
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + ch0)), is = __ldg(reinterpret_cast<const float4*>(invstd + ch0));
+  column_reduce2_v4(rows, c, rows_per_cta, [&](long long r, float4& a, float4& b) {
+    const float4 yv = __ldg(reinterpret_cast<const float4*>(y + r * ld_y + ch0));
+    const float4 dv = __ldg(reinterpret_cast<const float4*>(da + r * ld_da + ch0));
+    a.x = __fmaf_rn(yv.x, sc.x, sh.x) > 0.f ? dv.x : 0.f; b.x = a.x * (yv.x - mu.x) * is.x;
+    a.y = __fmaf_rn(yv.y, sc.y, sh.y) > 0.f ? dv.y : 0.f; b.y = a.y * (yv.y - mu.y) * is.y;
+    a.z = __fmaf_rn(yv.z, sc.z, sh.z) > 0.f ? dv.z : 0.f; b.z = a.z * (yv.z - mu.z) * is.z;
+    a.w = __fmaf_rn(yv.w, sc.w, sh.w) > 0.f ? dv.w : 0.f; b.w = a.w * (yv.w - mu.w) * is.w;
+  }, s1, s2);
+}
+
 // pooled upstream: the gradient of group g reaches only its arg-max row; "rows" of the reduction are groups
 __global__ void __launch_bounds__(RT)
 bn_bwd_stats_pool_kernel(long long groups, int ns, int c, int ld_y, int npoint, long long groups_per_cta,
@@ -238,6 +312,65 @@ bn_bwd_rows_kernel(long long rows, int c, int ld_da, int ld_y, const float* __re
     o[i] = (gamma ? __ldg(gamma + ch) : 1.f) * is * (d - corr);
   }
   store_rows8(dy, r, c, ch0, o, terms);
+}
+
+// The same with a thread's EIGHT channels fixed for its lifetime and its rows strided over the CTA's range: the
+// per-channel terms collapse into three coefficients held in registers (dY = ka dYhat + kb y + kc), the rows are
+// read and the upstream gradient fetched with 16-byte loads, two rows in flight.  Needs 16-byte aligned rows.
+__global__ void __launch_bounds__(RT)
+bn_bwd_rows_v8_kernel(long long rows, int c, int ld_da, int ld_y, long long rows_per_cta, const float* __restrict__ da,
+                      const float* __restrict__ dout_pm, const int* __restrict__ argmax, int ns,
+                      const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                      const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                      const double* __restrict__ s1, const double* __restrict__ s2, double count,
+                      __nv_bfloat16* __restrict__ dy, int terms) {
+  const int chunks = c >> 3, lanes = RT / chunks;
+  const int cx = threadIdx.x % chunks, ry = threadIdx.x / chunks;
+  if (ry >= lanes) return;
+  const int ch0 = cx << 3;
+  const float inv_count = count > 0.0 ? static_cast<float>(1.0 / count) : 0.f;
+  float sc[8], sh[8], ka[8], kb[8], kc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = ch0 + i;
+    const float is = __ldg(invstd + ch);
+    const float a = (gamma ? __ldg(gamma + ch) : 1.f) * is;
+    sc[i] = __ldg(scale + ch); sh[i] = __ldg(shift + ch);
+    // a (d - (s1 + (y - mean) is s2) / count)  =  a d  -  [a is s2 / count] y  +  [a is s2 mean / count - a s1 / count]
+    const float t2 = a * inv_count * static_cast<float>(s2[ch]) * is;
+    ka[i] = a; kb[i] = -t2;
+    kc[i] = __fmaf_rn(t2, __ldg(mean + ch), -(a * inv_count * static_cast<float>(s1[ch])));
+  }
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+#pragma unroll 2
+  for (long long r = r0 + ry; r < r1; r += lanes) {
+    const float4 ya = __ldg(reinterpret_cast<const float4*>(y + r * ld_y + ch0));
+    const float4 yb = __ldg(reinterpret_cast<const float4*>(y + r * ld_y + ch0) + 1);
+    const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+    float up[8];
+    if (da) {
+      const float4 d0 = __ldg(reinterpret_cast<const float4*>(da + r * ld_da + ch0));
+      const float4 d1 = __ldg(reinterpret_cast<const float4*>(da + r * ld_da + ch0) + 1);
+      up[0] = d0.x; up[1] = d0.y; up[2] = d0.z; up[3] = d0.w; up[4] = d1.x; up[5] = d1.y; up[6] = d1.z; up[7] = d1.w;
+    } else {
+      const long long g = r / ns;
+      const int slot = static_cast<int>(r - g * ns);
+      const long long oo = g * c + ch0;
+      const int4 a0 = __ldg(reinterpret_cast<const int4*>(argmax + oo)), a1 = __ldg(reinterpret_cast<const int4*>(argmax + oo) + 1);
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(dout_pm + oo)), p1 = __ldg(reinterpret_cast<const float4*>(dout_pm + oo) + 1);
+      up[0] = a0.x == slot ? p0.x : 0.f; up[1] = a0.y == slot ? p0.y : 0.f; up[2] = a0.z == slot ? p0.z : 0.f;
+      up[3] = a0.w == slot ? p0.w : 0.f; up[4] = a1.x == slot ? p1.x : 0.f; up[5] = a1.y == slot ? p1.y : 0.f;
+      up[6] = a1.z == slot ? p1.z : 0.f; up[7] = a1.w == slot ? p1.w : 0.f;
+    }
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = __fmaf_rn(yv[i], sc[i], sh[i]) > 0.f ? up[i] : 0.f;
+      o[i] = __fmaf_rn(ka[i], d, __fmaf_rn(kb[i], yv[i], kc[i]));
+    }
+    store_rows8(dy, r, c, ch0, o, terms);
+  }
 }
 
 // (b * n, ld) fp32 rows, columns [0, c) -> (b, c, n) slices of a channel-major tensor with batch stride `bstride`
@@ -414,6 +547,19 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgArgs a) {
   if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
 }
 
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// the 16-byte kernels: ONE wave of four CTAs per SM -- every CTA ends with a double atomic per channel on the same
+// 2 c addresses, and those serialise in L2, so fewer, longer CTAs (a thread still sums < 4096 values in fp32)
+long long pick_rows_per_cta_v4(long long rows, int c) {
+  const long long lanes = RT / (c / 4);
+  long long per = (rows + 4LL * sm_count() - 1) / (4LL * sm_count());
+  const long long cap = 4096 * lanes;
+  if (per > cap) per = cap;
+  if (per < lanes) per = lanes;
+  return per;
+}
+
 long long pick_rows_per_cta(long long rows, int c) {
   // enough CTAs to fill the machine, at most ~4096 values per thread partial (fp32 accumulation error)
   const long long lanes = RT / c > 0 ? RT / c : 1;
@@ -436,9 +582,13 @@ extern "C" int pn2_column_stats(long long rows, int c, int ld, const float* y, d
   PN2_RANGE("pn2_column_stats");
   if (rows <= 0) return PN2_OK;
   PN2_REQUIRE(c > 0 && c <= RT && ld >= c && y && sum && sumsq, "column_stats: bad arguments (c=%d must be <= %d)", c, RT);
-  const long long per = pick_rows_per_cta(rows, c);
-  const long long grid = (rows + per - 1) / per;
-  column_stats_kernel<<<static_cast<unsigned>(grid), RT, 0, as_stream(stream)>>>(rows, c, ld, per, y, sum, sumsq);
+  if (c % 4 == 0 && ld % 4 == 0 && aligned16(y)) {
+    const long long per = pick_rows_per_cta_v4(rows, c);
+    column_stats_v4_kernel<<<static_cast<unsigned>((rows + per - 1) / per), RT, 0, as_stream(stream)>>>(rows, c, ld, per, y, sum, sumsq);
+  } else {
+    const long long per = pick_rows_per_cta(rows, c);
+    column_stats_kernel<<<static_cast<unsigned>((rows + per - 1) / per), RT, 0, as_stream(stream)>>>(rows, c, ld, per, y, sum, sumsq);
+  }
   PN2_CHECK_LAUNCH("column_stats_kernel");
   return PN2_OK;
 }
@@ -496,9 +646,16 @@ extern "C" int pn2_bn_bwd_stats(long long rows, int c, int ld_da, int ld_y, cons
   if (rows <= 0) return PN2_OK;
   PN2_REQUIRE(c > 0 && c <= RT && y && scale && shift && mean && invstd && s1 && s2, "bn_bwd_stats: bad arguments");
   if (da) {
-    const long long per = pick_rows_per_cta(rows, c);
-    bn_bwd_stats_dense_kernel<<<static_cast<unsigned>((rows + per - 1) / per), RT, 0, as_stream(stream)>>>(
-        rows, c, ld_da, ld_y, per, da, y, scale, shift, mean, invstd, s1, s2);
+    if (c % 4 == 0 && ld_da % 4 == 0 && ld_y % 4 == 0 && aligned16(da) && aligned16(y) && aligned16(scale) &&
+        aligned16(shift) && aligned16(mean) && aligned16(invstd)) {
+      const long long per = pick_rows_per_cta_v4(rows, c);
+      bn_bwd_stats_dense_v4_kernel<<<static_cast<unsigned>((rows + per - 1) / per), RT, 0, as_stream(stream)>>>(
+          rows, c, ld_da, ld_y, per, da, y, scale, shift, mean, invstd, s1, s2);
+    } else {
+      const long long per = pick_rows_per_cta(rows, c);
+      bn_bwd_stats_dense_kernel<<<static_cast<unsigned>((rows + per - 1) / per), RT, 0, as_stream(stream)>>>(
+          rows, c, ld_da, ld_y, per, da, y, scale, shift, mean, invstd, s1, s2);
+    }
   } else {
     PN2_REQUIRE(dout_pm && argmax && ns > 0 && npoint > 0 && rows % ns == 0, "bn_bwd_stats: pooled upstream needs dout / argmax");
     const long long groups = rows / ns;
@@ -521,9 +678,21 @@ extern "C" int pn2_bn_bwd_rows(long long rows, int c, int ld_da, int ld_y, const
               "bn_bwd_rows: bad arguments");
   PN2_REQUIRE(da || (dout_pm && argmax && ns > 0 && npoint > 0), "bn_bwd_rows: no upstream gradient");
   const long long total = rows * (c / 8);
-  bn_bwd_rows_kernel<<<static_cast<unsigned>((total + RT - 1) / RT), RT, 0, as_stream(stream)>>>(
-      rows, c, ld_da, ld_y, da, dout_pm, argmax, ns, npoint, y, scale, shift, mean, invstd, gamma, s1, s2,
-      static_cast<double>(count), static_cast<__nv_bfloat16*>(dy_bf16), terms);
+  if (c <= 8 * RT && ld_y % 4 == 0 && aligned16(y) && aligned16(dy_bf16) &&
+      (da ? (ld_da % 4 == 0 && aligned16(da)) : (aligned16(dout_pm) && aligned16(argmax)))) {
+    // a CTA covers a contiguous range of rows: RT / (c / 8) of them per pass, enough CTAs for ~8 per SM
+    const long long lanes = RT / (c / 8);
+    long long per = (rows + 8LL * sm_count() - 1) / (8LL * sm_count());
+    per = (per + lanes - 1) / lanes * lanes;
+    if (per < 4 * lanes) per = 4 * lanes;
+    bn_bwd_rows_v8_kernel<<<static_cast<unsigned>((rows + per - 1) / per), RT, 0, as_stream(stream)>>>(
+        rows, c, ld_da, ld_y, per, da, dout_pm, argmax, ns, y, scale, shift, mean, invstd, gamma, s1, s2,
+        static_cast<double>(count), static_cast<__nv_bfloat16*>(dy_bf16), terms);
+  } else {
+    bn_bwd_rows_kernel<<<static_cast<unsigned>((total + RT - 1) / RT), RT, 0, as_stream(stream)>>>(
+        rows, c, ld_da, ld_y, da, dout_pm, argmax, ns, npoint, y, scale, shift, mean, invstd, gamma, s1, s2,
+        static_cast<double>(count), static_cast<__nv_bfloat16*>(dy_bf16), terms);
+  }
   PN2_CHECK_LAUNCH("bn_bwd_rows_kernel");
   return PN2_OK;
 }
