@@ -17,6 +17,10 @@
 //                                              shared memory, split over K = P across persistent CTAs
 //                        pn2_linear_bf16       dX = dY W (the same linear kernel, W^T packed as its weight)
 //   pn2_unpack_rows      (P, ld) fp32 rows -> the reference's (B, C, n) layout (gradient w.r.t. the grouped tensor)
+#include <cstdlib>
+
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through the runtime, libcuda is not linked)
+
 #include "tc.cuh"
 
 namespace pn2 {
@@ -547,7 +551,158 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgArgs a) {
   if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
 }
 
+// PN2_WGRAD_TMA=0 keeps the cp.async weight-gradient kernel (developer switch, A/B timing and parity)
+bool option_wgrad_tma() {
+  static int v = -1;
+  int r = __atomic_load_n(&v, __ATOMIC_RELAXED);
+  if (r < 0) {
+    const char* e = getenv("PN2_WGRAD_TMA");
+    r = (e && atoi(e) == 0) ? 0 : 1;
+    __atomic_store_n(&v, r, __ATOMIC_RELAXED);
+  }
+  return r != 0;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- the same contraction with the operand tiles fetched by TILED TMA (cp.async.bulk.tensor, SASS UTMALDG) --------
+// Each operand is described to the TMA unit as a 3-D tensor {channel, term, position} (strides: 2 bytes, one term
+// block, one row); a box of 64 channels x 1 term x 64 positions with SWIZZLE_128B lands in shared memory as exactly
+// the MN-major panel image above -- address generation, swizzle and the zero fill of channels >= c_out / c_in and of
+// positions >= rows happen in the copy engine.  Warp-specialised: lane 0 of warp 0 only issues copies (it runs as far
+// ahead as the ring has free stages), lane 0 of warp 1 only issues MMAs; full / empty mbarriers per stage
+// (expect_tx / tcgen05.commit) replace the per-chunk __syncthreads of the cp.async version, whose 128 threads spent
+// their time on address arithmetic for 16-byte copies and kept at most two chunks in flight (2-3 TB/s on the
+// SA1-sized layers).
+constexpr int WG_MAX_STAGES = 6;
+
+__global__ void __launch_bounds__(WG_THREADS)
+wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x, const WgArgs a,
+                 const int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[WG_MAX_STAGES], bar_empty[WG_MAX_STAGES], bar_done;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = 2u * 8192u, b_bytes = static_cast<uint32_t>(a.nt >> 6) * 8192u;
+  const uint32_t stage_bytes = static_cast<uint32_t>(a.terms) * (a_bytes + b_bytes);
+  const int n_prod = a.terms == 1 ? 1 : (a.terms == 2 ? 3 : 6);
+  const int co0 = blockIdx.y * 128, ci0 = blockIdx.z * a.nt;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(a.nt)) tmem_cols <<= 1;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(&bar_done, 1);
+    fence_mbar_init_cluster();
+    tc::tma_prefetch_desc(&tm_dy);
+    tc::tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_d = tmem_slot;
+  const uint32_t idesc = tc::idesc_bf16_f32(128, a.nt) | (1u << 15) | (1u << 16);  // both operands MN-major
+  const long long total_chunks = (a.rows + 63) / 64;
+  const long long c_first = static_cast<long long>(blockIdx.x) * a.chunks_per_cta;
+  long long c_last = c_first + a.chunks_per_cta;
+  if (c_last > total_chunks) c_last = total_chunks;
+  const int n_chunks = c_last > c_first ? static_cast<int>(c_last - c_first) : 0;
+  bool failed = false;
+  if (warp == 0) {
+    if (lane == 0) {  // ---- copy issue ----
+      for (int i = 0; i < n_chunks; ++i) {
+        const int s = i % stages, round = i / stages;
+        if (round > 0 && !mbar_wait(&bar_empty[s], (round - 1) & 1)) { failed = true; break; }
+        mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
+        const int row0 = static_cast<int>((c_first + i) * 64);
+        const uint32_t sa = base + s * stage_bytes, sb = sa + static_cast<uint32_t>(a.terms) * a_bytes;
+        for (int t = 0; t < a.terms; ++t) {
+          tc::tma_load_3d(sa + t * a_bytes, &tm_dy, co0, t, row0, &bar_full[s]);
+          tc::tma_load_3d(sa + t * a_bytes + 8192u, &tm_dy, co0 + 64, t, row0, &bar_full[s]);
+          for (int pnl = 0; pnl < (a.nt >> 6); ++pnl)
+            tc::tma_load_3d(sb + t * b_bytes + pnl * 8192u, &tm_x, ci0 + 64 * pnl, t, row0, &bar_full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issue ----
+      for (int i = 0; i < n_chunks; ++i) {
+        const int s = i % stages, round = i / stages;
+        if (!mbar_wait(&bar_full[s], round & 1)) { failed = true; break; }
+        tc::fence_after_sync();
+        const uint32_t sa = base + s * stage_bytes, sb = sa + static_cast<uint32_t>(a.terms) * a_bytes;
+        for (int pr = 0; pr < n_prod; ++pr) {
+          const uint32_t ta = sa + kWgProdDy[pr] * a_bytes, tb = sb + kWgProdX[pr] * b_bytes;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            tc::mma_bf16(tmem_d, smem_desc_mn_sw128(ta + kk * 2048), smem_desc_mn_sw128(tb + kk * 2048), idesc,
+                         (i > 0 || pr > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&bar_empty[s]);  // the stage is free once these MMAs have read it
+      }
+      if (!failed) tc::mma_commit(&bar_done);
+    }
+    __syncwarp();
+  }
+  if (failed) atomicExch(a.err, 2);  // (a lane that bailed out; the others below time out on bar_done)
+  if (n_chunks > 0) {
+    if (!mbar_wait(&bar_done, 0)) {
+      if (tid == 0) atomicExch(a.err, 2);
+    } else {
+      tc::fence_after_sync();
+      const int co = co0 + tid;  // thread = TMEM lane = output channel
+      const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
+      for (int c0 = 0; c0 < a.nt; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(lane_base + c0, v);
+        if (co < a.c_out) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int ci = ci0 + c0 + i;
+            if (ci < a.c_in) atomicAdd(a.dw + static_cast<long long>(co) * a.c_in + ci, v[i]);
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link dependency on libcuda)
+EncodeTiledFn tensor_map_encoder() {
+  static void* cached = nullptr;
+  void* p = __atomic_load_n(&cached, __ATOMIC_ACQUIRE);
+  if (p) return reinterpret_cast<EncodeTiledFn>(p);
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  __atomic_store_n(&cached, p, __ATOMIC_RELEASE);
+  return reinterpret_cast<EncodeTiledFn>(p);
+}
+
+// {channel, term, position} view of split-precision operand rows: `valid` channels per term block, blocks `blk`
+// elements apart, rows `ld` elements apart; boxes of 64 channels x 1 term x 64 positions, SWIZZLE_128B
+bool encode_rows_map(CUtensorMap* tm, const void* ptr, long long rows, int valid, int terms, int blk, int ld) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc || rows <= 0 || rows >= (1LL << 31) || valid <= 0) return false;
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(valid), static_cast<cuuint64_t>(terms), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(blk) * 2, static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[3] = {64, 1, 64}, estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // the 16-byte kernels: ONE wave of four CTAs per SM -- every CTA ends with a double atomic per channel on the same
 // 2 c addresses, and those serialise in L2, so fewer, longer CTAs (a thread still sums < 4096 values in fp32)
@@ -736,9 +891,25 @@ static int wgrad_launch(long long rows, int c_out, int c_in, int ld_dy, int ld_x
   a.chunks_per_cta = (chunks + ctas - 1) / ctas;
   ctas = (chunks + a.chunks_per_cta - 1) / a.chunks_per_cta;
   const size_t stage = static_cast<size_t>(terms) * (2 * 8192 + static_cast<size_t>(nt / 64) * 8192);
+  dim3 grid(static_cast<unsigned>(ctas), ny, nz);
+  // tiled TMA path: the operands as {channel, term, position} tensor maps (needs rows laid out as whole term blocks)
+  CUtensorMap tm_dy, tm_x;
+  const int ci_valid = (c_in + 7) & ~7;
+  if (option_wgrad_tma() && ld_dy % nblk == 0 && a.blk_dy * nblk <= ld_dy &&
+      encode_rows_map(&tm_dy, dy_bf16, rows, c_out, terms, a.blk_dy, ld_dy) &&
+      encode_rows_map(&tm_x, x_bf16, rows, ci_valid, terms, a.blk_x, ld_x)) {
+    int stages = static_cast<int>((225 * 1024) / stage);
+    if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
+    if (stages >= 2) {
+      const size_t smem = stages * stage + 1024;
+      PN2_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      wgrad_tma_kernel<<<grid, WG_THREADS, smem, as_stream(stream)>>>(tm_dy, tm_x, a, stages);
+      PN2_CHECK_LAUNCH("wgrad_tma_kernel");
+      return PN2_OK;
+    }
+  }
   const size_t smem = 2 * stage + 1024;
   PN2_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  dim3 grid(static_cast<unsigned>(ctas), ny, nz);
   wgrad_kernel<<<grid, WG_THREADS, smem, as_stream(stream)>>>(a);
   PN2_CHECK_LAUNCH("wgrad_kernel");
   return PN2_OK;

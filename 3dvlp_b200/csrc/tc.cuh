@@ -88,6 +88,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// Tiled (tensor-map) TMA load of one 3-D box global -> shared, completion on an mbarrier.  `tmap` is the generic
+// address of a CUtensorMap kernel parameter (__grid_constant__); coordinates are in elements, innermost first.
+// Out-of-bounds parts of the box are written as zeros and still count towards the transaction bytes.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;  // src-size 0 -> the 16 bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
