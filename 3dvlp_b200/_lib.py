@@ -81,7 +81,8 @@ def _call(L, fn, name, args, device):
 def set_option(name, value):
     """pn2_set_option: "fps_bucket" (0 = low-latency cluster FPS, 1 = single-SM bucketed FPS for
     throughput with several batches in flight), "bq_grid" (hashed-grid ball query on/off),
-    "sa_tiles_per_group" (0 = one fused-SA CTA per SM slot; k > 0 = fewer CTAs, >= k tiles per group)."""
+    "sa_tiles_per_group" (0 = one fused-SA CTA per SM slot; k > 0 = fewer CTAs, >= k tiles per group),
+    "wgrad_tma" (1 = training weight gradient fed by tiled TMA, 0 = cp.async copies)."""
     L = lib()
     if L.pn2_set_option(name.encode(), int(value)) != 0:
         raise Pn2Error(L.pn2_last_error().decode())

@@ -73,18 +73,19 @@ int* device_err_flag() {
 // ---- host-side statistics (pn2_get_stat): which kernel variant a call really launched ------------
 static const char* const kStatName[STAT_COUNT] = {"fps_cluster_launches", "fps_bucket_launches", "fps_pair_launches",
                                                    "bq_grid_launches", "bq_small_grid_launches", "bq_scan_launches",
-                                                   "nn_small_launches", "nn_tiled_launches"};
+                                                   "nn_small_launches", "nn_tiled_launches", "wgrad_tma_launches",
+                                                   "wgrad_cpasync_launches"};
 static long long g_stat[STAT_COUNT] = {0};
 void stat_add(Stat s, long long v) { __atomic_fetch_add(&g_stat[s], v, __ATOMIC_RELAXED); }
 
 // ---- run-time options ----------------------------------------------------------------------------
-static const char* const kOptName[OPT_COUNT] = {"fps_bucket", "bq_grid", "sa_tiles_per_group"};
-static const char* const kOptEnv[OPT_COUNT] = {"PN2_FPS_BUCKET", "PN2_BQ_GRID", "PN2_SA_TILES_PER_GROUP"};
-static const int kOptDefault[OPT_COUNT] = {0, 1, 0};
-static int g_opt[OPT_COUNT] = {-1, -1, -1};
+static const char* const kOptName[OPT_COUNT] = {"fps_bucket", "bq_grid", "sa_tiles_per_group", "wgrad_tma"};
+static const char* const kOptEnv[OPT_COUNT] = {"PN2_FPS_BUCKET", "PN2_BQ_GRID", "PN2_SA_TILES_PER_GROUP", "PN2_WGRAD_TMA"};
+static const int kOptDefault[OPT_COUNT] = {0, 1, 0, 1};
+static int g_opt[OPT_COUNT] = {-1, -1, -1, -1};
 // per-thread override (pn2_set_option_thread): -1 = follow the process-wide value.  A host thread that
 // captures a CUDA graph with other settings does not disturb calls made by other threads meanwhile.
-static thread_local int t_opt[OPT_COUNT] = {-1, -1, -1};
+static thread_local int t_opt[OPT_COUNT] = {-1, -1, -1, -1};
 
 int option_value(Option o) {
   if (t_opt[o] >= 0) return t_opt[o];
@@ -107,7 +108,7 @@ extern "C" int pn2_set_option(const char* name, int value) {
       return PN2_OK;
     }
   }
-  pn2::set_error("set_option: unknown option '%s' (known: fps_bucket, bq_grid, sa_tiles_per_group)", name ? name : "(null)");
+  pn2::set_error("set_option: unknown option '%s' (known: fps_bucket, bq_grid, sa_tiles_per_group, wgrad_tma)", name ? name : "(null)");
   return PN2_ERR_INVALID;
 }
 

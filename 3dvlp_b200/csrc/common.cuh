@@ -55,13 +55,13 @@ int sm_count();
 void keep_workspace_pool();
 
 // run-time options (pn2_set_option); initial values come from the environment
-enum Option { OPT_FPS_BUCKET = 0, OPT_BQ_GRID = 1, OPT_SA_TILES_PER_GROUP = 2, OPT_COUNT = 3 };
+enum Option { OPT_FPS_BUCKET = 0, OPT_BQ_GRID = 1, OPT_SA_TILES_PER_GROUP = 2, OPT_WGRAD_TMA = 3, OPT_COUNT = 4 };
 int option_value(Option o);
 
 // host-side launch statistics, read back with pn2_get_stat(name): the parity tests assert through them
 // that the kernel variant they mean to cover is the one that ran
 enum Stat { STAT_FPS_CLUSTER = 0, STAT_FPS_BUCKET, STAT_FPS_PAIR, STAT_BQ_GRID, STAT_BQ_SMALL_GRID, STAT_BQ_SCAN,
-            STAT_NN_SMALL, STAT_NN_TILED, STAT_COUNT };
+            STAT_NN_SMALL, STAT_NN_TILED, STAT_WGRAD_TMA, STAT_WGRAD_CPASYNC, STAT_COUNT };
 void stat_add(Stat s, long long v = 1);
 
 // NVTX range around every C-ABI entry point (header-only NVTX3: the tools library is looked up at run

@@ -551,18 +551,6 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgArgs a) {
   if (warp == 0) tc::tmem_dealloc(tmem_d, tmem_cols);
 }
 
-// PN2_WGRAD_TMA=0 keeps the cp.async weight-gradient kernel (developer switch, A/B timing and parity)
-bool option_wgrad_tma() {
-  static int v = -1;
-  int r = __atomic_load_n(&v, __ATOMIC_RELAXED);
-  if (r < 0) {
-    const char* e = getenv("PN2_WGRAD_TMA");
-    r = (e && atoi(e) == 0) ? 0 : 1;
-    __atomic_store_n(&v, r, __ATOMIC_RELAXED);
-  }
-  return r != 0;
-}
-
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---- the same contraction with the operand tiles fetched by TILED TMA (cp.async.bulk.tensor, SASS UTMALDG) --------
@@ -895,7 +883,7 @@ static int wgrad_launch(long long rows, int c_out, int c_in, int ld_dy, int ld_x
   // tiled TMA path: the operands as {channel, term, position} tensor maps (needs rows laid out as whole term blocks)
   CUtensorMap tm_dy, tm_x;
   const int ci_valid = (c_in + 7) & ~7;
-  if (option_wgrad_tma() && ld_dy % nblk == 0 && a.blk_dy * nblk <= ld_dy &&
+  if (option_value(OPT_WGRAD_TMA) && ld_dy % nblk == 0 && a.blk_dy * nblk <= ld_dy &&
       encode_rows_map(&tm_dy, dy_bf16, rows, c_out, terms, a.blk_dy, ld_dy) &&
       encode_rows_map(&tm_x, x_bf16, rows, ci_valid, terms, a.blk_x, ld_x)) {
     int stages = static_cast<int>((225 * 1024) / stage);
@@ -905,6 +893,7 @@ static int wgrad_launch(long long rows, int c_out, int c_in, int ld_dy, int ld_x
       PN2_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
       wgrad_tma_kernel<<<grid, WG_THREADS, smem, as_stream(stream)>>>(tm_dy, tm_x, a, stages);
       PN2_CHECK_LAUNCH("wgrad_tma_kernel");
+      stat_add(STAT_WGRAD_TMA);
       return PN2_OK;
     }
   }
@@ -912,6 +901,7 @@ static int wgrad_launch(long long rows, int c_out, int c_in, int ld_dy, int ld_x
   PN2_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   wgrad_kernel<<<grid, WG_THREADS, smem, as_stream(stream)>>>(a);
   PN2_CHECK_LAUNCH("wgrad_kernel");
+  stat_add(STAT_WGRAD_CPASYNC);
   return PN2_OK;
 }
 

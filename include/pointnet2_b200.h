@@ -39,7 +39,8 @@ int pn2_device_arch(int* major, int* minor); /* compute capability of the curren
 int pn2_poll_device_error(int* flag_out, void* stream);
 /* Host-side launch statistics (process-wide, monotonic): how often a kernel variant was chosen --
  * "fps_cluster_launches", "fps_bucket_launches", "fps_pair_launches", "bq_grid_launches",
- * "bq_small_grid_launches", "bq_scan_launches", "nn_small_launches", "nn_tiled_launches".
+ * "bq_small_grid_launches", "bq_scan_launches", "nn_small_launches", "nn_tiled_launches",
+ * "wgrad_tma_launches", "wgrad_cpasync_launches".
  * The parity tests read them to prove that the variant they mean to cover is the one that ran.
  * Returns -1 for an unknown name. */
 long long pn2_get_stat(const char* name);
@@ -51,7 +52,10 @@ long long pn2_get_stat(const char* name);
  *   "sa_tiles_per_group" [PN2_SA_TILES_PER_GROUP, default 0]  k > 0 = pn2_sa_group_mlp launches fewer
  *                persistent CTAs, each 128-thread group claiming >= k row tiles, so the per-CTA prologue
  *                (weight TMA, TMEM allocation) is paid less often: same output, longer single launch,
- *                less SM-time (throughput mode: several batches in flight).
+ *                less SM-time (throughput mode: several batches in flight);
+ *   "wgrad_tma"  [PN2_WGRAD_TMA, default 1]   0 = pn2_wgrad_*_bf16 keeps the cp.async operand copies instead of
+ *                the tiled-TMA (tensor-map) kernel: same result; also the automatic fallback when a tensor map
+ *                cannot be encoded.
  * pn2_get_option returns the value, or -1 for an unknown name. */
 int pn2_set_option(const char* name, int value);
 int pn2_get_option(const char* name);

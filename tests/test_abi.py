@@ -130,6 +130,7 @@ def test_options_are_process_wide_with_a_per_thread_override(pkg):
         assert pkg.get_option("bq_grid") == 0
     finally:
         pkg.set_option("bq_grid", 1)
+    assert pkg.get_option("wgrad_tma") == 1   # tiled-TMA weight gradient is the default
     with pytest.raises(pkg._lib.Pn2Error):
         pkg.set_option("no_such_option", 1)
     with pytest.raises(pkg._lib.Pn2Error):
@@ -138,7 +139,8 @@ def test_options_are_process_wide_with_a_per_thread_override(pkg):
 
 def test_launch_statistics_are_exposed(pkg):
     for name in ("fps_cluster_launches", "fps_bucket_launches", "bq_grid_launches", "bq_small_grid_launches",
-                 "bq_scan_launches", "nn_small_launches", "nn_tiled_launches"):
+                 "bq_scan_launches", "nn_small_launches", "nn_tiled_launches", "wgrad_tma_launches",
+                 "wgrad_cpasync_launches"):
         assert pkg.get_stat(name) >= 0
     with pytest.raises(pkg._lib.Pn2Error):
         pkg.get_stat("no_such_statistic")

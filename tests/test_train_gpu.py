@@ -228,9 +228,21 @@ def _split_rows(a, terms):
     return torch.cat([t[i] for i in order], dim=1).contiguous(), t
 
 
+@pytest.fixture(params=[1, 0], ids=["tma", "cpasync"])
+def wgrad_variant(request, pkg):
+    """Both operand-copy variants of the weight-gradient kernel (option "wgrad_tma"): tiled TMA through tensor
+    maps (the default) and the cp.async fallback; the launch statistics prove which one ran."""
+    name = "wgrad_tma_launches" if request.param else "wgrad_cpasync_launches"
+    pkg.set_option("wgrad_tma", request.param)
+    before = pkg.get_stat(name)
+    yield request.param
+    pkg.set_option("wgrad_tma", 1)
+    assert pkg.get_stat(name) > before, "%s did not move: the other kernel variant ran" % name
+
+
 @pytest.mark.parametrize("terms", [1, 2, 3])
 @pytest.mark.parametrize("rows,c_out,c_in", [(5000, 64, 4), (4100, 128, 64), (3000, 256, 259), (130, 64, 131)])
-def test_wgrad_split_one_launch(pkg, cuda, terms, rows, c_out, c_in):
+def test_wgrad_split_one_launch(pkg, cuda, wgrad_variant, terms, rows, c_out, c_in):
     """pn2_wgrad_split_bf16: every leading (dy term, x term) product of the split-precision weight gradient in one
     launch, accumulated in one TMEM tile -- against the fp64 sum of the same bf16 term products (the contraction is
     exact up to fp32 accumulation) and against one pn2_wgrad_bf16 call per product."""
