@@ -119,7 +119,47 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const LinArgs a) {
     // ---- epilogue: thread t <-> row t (TMEM lane), 16 columns at a time ----------------------
     const int r = row0 + tid;
     const uint32_t lane_base = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
-    for (int c0 = 0; c0 < a.n; c0 += 16) {
+    int c_begin = 0;
+    if (a.out_mode == 0) {
+      // fp32 rows, 32 columns at a time through a per-warp 4 KB staging tile in the (now idle) operand ring: a
+      // thread holds ONE row, so storing straight from registers makes every warp store 32 separate 16-byte
+      // pieces 4 n bytes apart -- the L2 write-request rate, not HBM, bounded the wide training layers (537 MB
+      // of Y in 303 us).  Staged, eight lanes write one row's 128 contiguous bytes: 4 full lines per instruction.
+      // (All MMAs have completed -- the wait above -- so nothing reads the ring any more.)
+      const int lane = tid & 31;
+      const uint32_t st = base + static_cast<uint32_t>(warp) * 4096u;
+      float* yrow = static_cast<float*>(a.y);
+      for (int c0 = 0; c0 + 32 <= a.n; c0 += 32) {
+        float v[32];
+        tc::tmem_ld16(lane_base + c0, *reinterpret_cast<float(*)[16]>(v));
+        tc::tmem_ld16(lane_base + c0 + 16, *reinterpret_cast<float(*)[16]>(v + 16));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] += s_bias[c0 + i];
+          if (a.relu) v[i] = fmaxf(v[i], 0.f);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st + lane * 128u + (((ch ^ lane) & 7) << 4)),
+                       "f"(v[4 * ch]), "f"(v[4 * ch + 1]), "f"(v[4 * ch + 2]), "f"(v[4 * ch + 3])
+                       : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3), ch = lane & 7;
+          float4 o;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                       : "r"(st + rr * 128u + (((ch ^ rr) & 7) << 4))
+                       : "memory");
+          const int gr = row0 + warp * 32 + rr;
+          if (gr < a.m) *reinterpret_cast<float4*>(yrow + static_cast<size_t>(gr) * a.n + c0 + ch * 4) = o;
+        }
+        __syncwarp();
+        c_begin = c0 + 32;
+      }
+    }
+    for (int c0 = c_begin; c0 < a.n; c0 += 16) {
       float v[16];
       tc::tmem_ld16(lane_base + c0, v);
 #pragma unroll
