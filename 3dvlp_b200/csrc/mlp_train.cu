@@ -13,10 +13,14 @@
 //   backward, per layer  pn2_bn_bwd_stats      s1 = sum dYhat, s2 = sum dYhat xhat  (dYhat = upstream masked by ReLU;
 //                                              the last layer's upstream is the pooled gradient at the arg-max slot)
 //                        pn2_bn_bwd_rows       dY = gamma invstd (dYhat - s1/P - xhat s2/P)  -> bf16 rows
-//                        pn2_wgrad_bf16        dW = dY^T X on tcgen05: MN-major operands, rows copied as they are into
-//                                              shared memory, split over K = P across persistent CTAs
+//                        pn2_wgrad_bf16        dW = dY^T X on tcgen05: MN-major operands, the rows fetched as they are by
+//                                              tiled TMA (tensor maps {channel, term, position}; cp.async fallback),
+//                                              split over K = P across persistent CTAs
 //                        pn2_linear_bf16       dX = dY W (the same linear kernel, W^T packed as its weight)
 //   pn2_unpack_rows      (P, ld) fp32 rows -> the reference's (B, C, n) layout (gradient w.r.t. the grouped tensor)
+// The elementwise / reduction kernels are HBM-bound: 16-byte loads with a thread's channels fixed for its lifetime
+// (per-channel terms in registers), rows strided over a CTA's contiguous range; each exists in a scalar form for
+// rows that are not 16-byte aligned.
 #include <cstdlib>
 
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through the runtime, libcuda is not linked)
