@@ -61,3 +61,65 @@ def test_committed_bench_line_has_every_contract_key():
     assert d["e2e"]["value"] < d["value"]                             # the copies are inside the timed region
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_final_bench_line_of_round_2_has_every_contract_key():
+    d = _json_lines(open(os.path.join(ROOT, "profiles", "bench_r02_final.json")).read())[-1]
+    assert BASE_KEYS | {"clocks", "roofline", "cpu_baseline"} <= set(d)
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["vs_baseline"] is None
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "fp32-alu/latency"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert d["clocks"]["samples_before_region_end"] >= 1 and not d["clocks"]["reasons"]
+    assert d["e2e"]["value"] < d["value"] and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["train_step"]["graphed"]["ms_per_step"] < d["train_step"]["ms_per_step"]
+
+
+class _FakeNvml:
+    NVML_CLOCK_SM = 0
+
+    def __init__(self):
+        self.calls = 0
+
+    def nvmlDeviceGetClockInfo(self, h, which):
+        self.calls += 1
+        return 1965
+
+    def nvmlDeviceGetCurrentClocksEventReasons(self, h):
+        return 0x4   # sw_power_cap
+
+
+class _FakeEvent:
+    """query() turns True on its third call: the timed region 'ends' after two in-region samples."""
+
+    def __init__(self):
+        self.n = 0
+
+    def query(self):
+        self.n += 1
+        return self.n >= 3
+
+
+def test_clock_sampler_counts_only_samples_taken_inside_the_region():
+    """bench.ClockSampler.sample_until: the main thread samples NVML between the last enqueue and the closing
+    synchronisation; a sample counts as in-region only while the closing event is still pending."""
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler(0)
+    s.nv, s.h, s.max_mhz = _FakeNvml(), object(), 1965.0
+    s.sample_until(_FakeEvent(), period_s=0.0)
+    out = s.stop()
+    assert out["samples"] == 3 and out["samples_before_region_end"] == 2
+    assert out["sm_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+
+
+def test_graphed_train_step_refuses_a_non_capturable_optimizer():
+    """graph.GraphedTrainStep checks the optimizer before it touches the device."""
+    import importlib
+    import pytest
+    import torch
+    sys.path.insert(0, ROOT)
+    pkg = importlib.import_module("3dvlp_b200")
+    lin = torch.nn.Linear(2, 2)
+    with pytest.raises(RuntimeError, match="capturable"):
+        pkg.GraphedTrainStep(lambda: lin(torch.zeros(1, 2)).sum(), torch.optim.Adam(lin.parameters(), lr=1e-3))
