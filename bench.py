@@ -15,6 +15,11 @@ A "step" is one eval-mode forward of the backbone over one batch of 8 scenes per
   roofline     the dominant kernel (SA1 furthest-point sampling) + per-op table in roofline_ops
   cpu_baseline the CPU oracle (reference op semantics restated in C + the reference's torch layers)
                timed on this box's host cores on a bounded sample (rank 0, N = 1 only)
+  clocks       SM clock / throttle reasons sampled through NVML by the main thread while the timed region is still
+               running on the GPU (after its last enqueue, before its closing synchronisation)
+  timed_region_attempts / host_issue_ms   W warm-up + exactly K timed steps per attempt; a region the host could not
+               keep fed (enqueue > 35 % of its device time) is measured again, at most twice, all attempts listed
+  grounding_step_forward / train_step (eager and as ONE CUDA graph) / votenet_* / ref_cuda_ext / numerics   extra legs
 """
 import argparse
 import gc
